@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the splat forward-render path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload C2]
+
+One "step" = one forward render of one camera view of the workload scene (per rank).
+N == 1 : BASELINE.json configs[1]  — synthetic 3.3M-Gaussian SH3 scene, 1920x1080, single camera.
+N  > 1 : configs[3] — camera views of that scene sharded across ranks (view v -> rank v % N),
+         every rank holds the full scene, no collective on the data path ("weak": one view per
+         rank per step).  `--gather` additionally times an NCCL gather of the frames to rank 0.
+
+Printed by rank 0 as ONE JSON line:
+  value      frames/s, whole job, scene + cameras resident in HBM, through the C ABI
+             (gsr_renderer_render: two alternating streams per GPU hide the num_rendered read-back)
+  e2e        same metric through the public host-buffer call (gsr_renderer_render_host): per step a
+             144-byte camera H2D from pinned memory and the full fp32 frame D2H into pinned memory
+  roofline   the dominant HBM-bound kernel, timed live with the library's CUDA events
+  stages     per-stage ms of one frame (events on the launching stream) + achieved GB/s
+  cpu_baseline  the CPU oracle ("port") timed on this box's host cores on a bounded sample
+`--impl reference` times the reference's CPU implementation of the path (the oracle port; the
+upstream CUDA rasterizer is absent from the reference tree and the in-tree one is GPU code).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "frames/s @3.3M Gaussians SH3 1080p (views/s when sharded across GPUs)"
+WORKLOADS = {
+    "C1": "synthetic 100k-Gaussian SH3 scene, 1280x720, single camera",
+    "C2": "synthetic 3.3M-Gaussian SH3 scene (bicycle-scale), 1920x1080, single camera",
+    "C3": "synthetic 6M-Gaussian SH3 scene, 3840x2160, single camera",
+    "C4": "camera-view batch over the synthetic 3.3M-Gaussian SH3 scene, 1920x1080, sharded across GPUs",
+    "C5": "dense low-opacity 2M-Gaussian scene, precomputed colours, 1920x1080",
+}
+
+
+def algorithmic_bytes(P_visible, P_culled, R, tiles, passes, precomp):
+    """SURVEY.md §8(d) per-unit figures."""
+    per_vis = (44 + 12 + 48) if precomp else 284
+    return {
+        "preprocess": per_vis * P_visible + 20 * P_culled,
+        "scan": 0,
+        "duplicate": 20 * P_visible + 12 * R,
+        "sort": (8 + passes * 24) * R,
+        "sort_pass": 24 * R,
+        "ranges": 8 * R + 8 * tiles,
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.proc = None
+        self.lines = []
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference(workload, frames, threads=None, P=None):
+    """Time the CPU implementation of the path (oracle port) on `frames` full frames."""
+    from gsrast_b200 import camera, scene
+    from oracle import gsr_oracle
+
+    sc, cfg = scene.make_config_scene("C2" if workload == "C4" else workload, P=P)
+    cam = camera.default_camera(cfg["W"], cfg["H"])
+    threads = threads or gsr_oracle.hardware_threads()
+    times, stage = [], None
+    for _ in range(max(1, frames)):
+        r = gsr_oracle.forward_scene(sc, cam, threads=threads)
+        times.append(r.timings["total"])
+        stage = r.timings
+    return dict(ms=[t * 1e3 for t in times], threads=threads, R=r.num_rendered, stage=stage, P=sc.P, cfg=cfg)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.time()
+    res = cpu_reference(args.workload, args.warmup + args.steps)
+    ms = res["ms"][args.warmup:]
+    mean_ms = sum(ms) / len(ms)
+    fps = 1e3 / mean_ms
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean_ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload], "name": args.workload, "P": res["P"],
+                   "width": res["cfg"]["W"], "height": res["cfg"]["H"], "num_rendered": res["R"]},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": res["threads"], "kind": "port",
+                         "sample": "%d full %s frame(s); CPU port of the reference path (upstream CUDA rasterizer "
+                                   "absent from the tree; in-tree gscuda is GPU-only code)" % (len(ms), args.workload)},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "stage_ms": {k: v * 1e3 for k, v in res["stage"].items()},
+        "wall_s": time.time() - t0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
+    ap.add_argument("--gather", action="store_true", help="also time the NCCL gather of frames to rank 0 (N>1)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=3)
+    ap.add_argument("--simple-blend", action="store_true")
+    ap.add_argument("--P", type=int, default=None, help="override the Gaussian count (debug only; invalidates the metric)")
+    args = ap.parse_args()
+    if args.workload is None:
+        args.workload = "C2" if args.gpus == 1 else "C4"
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+
+    from gsrast_b200 import _lib, camera, scene
+    from gsrast_b200.views import ViewRenderer, gather_frames, shard_views
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    _lib.lib()  # fail loudly if the extension is missing
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    K, Wm = args.steps, max(args.warmup, 3)
+
+    base = "C2" if args.workload == "C4" else args.workload
+    sc, cfg = scene.make_config_scene(base, P=args.P)
+    W, H = cfg["W"], cfg["H"]
+    flags = _lib.FLAG_BLEND_SIMPLE if args.simple_blend else 0
+    t_up = time.time()
+    vr = ViewRenderer.from_scene(sc, W, H, device=dev, flags=flags)
+    torch.cuda.synchronize()
+    upload_s = time.time() - t_up
+
+    if world == 1 and args.workload != "C4":
+        cams = [camera.default_camera(W, H)] * (K + Wm)
+    else:
+        # C4: orbit poses; rank r renders views r, r+N, ... -> K + warm-up views per rank
+        allc = camera.orbit_cameras((K + Wm) * world, W, H)
+        cams = [allc[i] for i in shard_views(len(allc), rank, world)]
+    tanx, tany = cams[0].tan_fovx, cams[0].tan_fovy
+    packed = np.stack([c.packed() for c in cams]).astype(np.float32)
+    frame_bytes = 3 * W * H * 4
+    nbuf = min(K, 8)  # device output ring for the resident-input measurement
+    out_dev = torch.empty((nbuf, 3, H, W), dtype=torch.float32, device=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def render_resident(cam_block):
+        # K frames in blocks of nbuf so the output ring is reused (writes stay device-side)
+        total = 0
+        for i in range(0, cam_block.shape[0], nbuf):
+            blk = cam_block[i:i + nbuf]
+            _, nr = vr.render(blk, tanx, tany, out=out_dev[: blk.shape[0]])
+            total += sum(nr)
+        return total
+
+    # ---------------- resident-input throughput (value) -----------------------------------
+    render_resident(packed[:Wm])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    render_resident(packed[Wm:Wm + K])
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---------------- end to end with host buffers (e2e) -----------------------------------
+    host_out = torch.empty((nbuf, 3, H, W), dtype=torch.float32).pin_memory()
+
+    def render_e2e(cam_block):
+        for i in range(0, cam_block.shape[0], nbuf):
+            blk = cam_block[i:i + nbuf]
+            vr.render_host(blk, tanx, tany, out_host=host_out[: blk.shape[0]])
+
+    render_e2e(packed[:Wm])
+    barrier()
+    t0 = time.perf_counter()
+    render_e2e(packed[Wm:Wm + K])
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    checksum = float(host_out[0].double().mean())
+
+    # ---------------- optional NCCL gather of frames to rank 0 -----------------------------
+    gather_ms = None
+    if args.gather and dist is not None:
+        local = torch.empty((K, 3, H, W), dtype=torch.float32, device=dev)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        vr.render(packed[Wm:Wm + K], tanx, tany, out=local)
+        gather_frames(local, K * world, rank, world, dst=0)
+        g1.record()
+        barrier()
+        gather_ms = g0.elapsed_time(g1)
+
+    if dist is not None:
+        t = torch.tensor([dev_ms, e2e_ms, gather_ms or 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms, gmax = [float(x) for x in t.cpu()]
+        gather_ms = gmax if gather_ms is not None else None
+
+    # ---------------- per-stage device times + roofline (rank 0) ----------------------------
+    if rank == 0:
+        stage_runs = []
+        for i in range(6):
+            _, _, tm = vr.render(packed[Wm:Wm + 1], tanx, tany, out=out_dev[:1], timings=True)
+            if i >= 2:
+                stage_runs.append(tm)
+        keys = ("preprocess_ms", "scan_ms", "duplicate_ms", "sort_ms", "ranges_ms", "blend_ms", "total_ms",
+                "sort_hist_ms")
+        st = {k: statistics.mean(r[k] for r in stage_runs) for k in keys}
+        passes = stage_runs[0]["sort_passes"]
+        pass_ms = [statistics.mean(r["sort_pass_ms"][i] for r in stage_runs) for i in range(passes)]
+        R = stage_runs[0]["num_rendered"]
+        launches_per_frame = stage_runs[0]["kernel_launches"]
+        # visible count from the geometry state of lane 0 is not exposed; recompute cheaply on the device
+        from gsrast_b200 import rasterizer as Rz
+
+        g = Rz.GSGaussians(W, H, device=dev, use_rects=False, flags=flags)
+        g.configure_from_splat_data(sc)
+        g.draw(cams[Wm])
+        torch.cuda.synchronize()
+        P_vis = int((g.map_geometry_state()["internal_radii"] > 0).sum().item())
+        n_eval = None
+        del g
+        torch.cuda.empty_cache()
+        tiles = ((W + 15) // 16) * ((H + 15) // 16)
+        ab = algorithmic_bytes(P_vis, sc.P - P_vis, R, tiles, passes, sc.colors_precomp is not None)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+
+        def gbs(b, ms):
+            return (b / 1e9) / (ms / 1e3) if ms and ms > 0 else None
+
+        stages = {
+            "preprocess": {"ms": st["preprocess_ms"], "GB/s": gbs(ab["preprocess"], st["preprocess_ms"])},
+            "scan": {"ms": st["scan_ms"]},
+            "duplicate": {"ms": st["duplicate_ms"], "GB/s": gbs(ab["duplicate"], st["duplicate_ms"])},
+            "sort": {"ms": st["sort_ms"], "GB/s": gbs(ab["sort"], st["sort_ms"]), "hist_ms": st["sort_hist_ms"],
+                     "pass_ms": pass_ms, "passes": passes},
+            "ranges": {"ms": st["ranges_ms"], "GB/s": gbs(ab["ranges"], st["ranges_ms"])},
+            "blend": {"ms": st["blend_ms"]},
+            "frame_serial_ms": st["total_ms"],
+        }
+        for v in stages.values():
+            if isinstance(v, dict) and v.get("GB/s"):
+                v["frac_of_peak"] = v["GB/s"] / peak
+        pre_sort_b = ab["preprocess"] + ab["duplicate"] + ab["sort"] + ab["ranges"]
+        pre_sort_ms = st["preprocess_ms"] + st["scan_ms"] + st["duplicate_ms"] + st["sort_ms"] + st["ranges_ms"]
+        stages["preprocess_plus_sort"] = {"ms": pre_sort_ms, "GB/s": gbs(pre_sort_b, pre_sort_ms),
+                                          "frac_of_peak": gbs(pre_sort_b, pre_sort_ms) / peak}
+        # dominant HBM kernel: a single launch — preprocess, or the mean onesweep pass
+        cand = {"preprocess_kernel": (ab["preprocess"], st["preprocess_ms"]),
+                "onesweep_kernel (mean of %d digit passes)" % passes: (ab["sort_pass"], statistics.mean(pass_ms)),
+                "duplicate_kernel": (ab["duplicate"], st["duplicate_ms"])}
+        share = {"preprocess_kernel": st["preprocess_ms"], "duplicate_kernel": st["duplicate_ms"]}
+        share["onesweep_kernel (mean of %d digit passes)" % passes] = sum(pass_ms)
+        dom = max(share, key=share.get)
+        roof = {"bound": "hbm", "kernel": dom, "achieved": gbs(*cand[dom]), "peak": peak, "unit": "GB/s",
+                "frac": gbs(*cand[dom]) / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": cand[dom][0], "ms_per_launch": cand[dom][1],
+                "share_of_frame": share[dom] / st["total_ms"]}
+        ncu_traffic = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(ncu_traffic):
+            try:
+                roof["traffic"] = json.load(open(ncu_traffic)).get(dom.split(" ")[0])
+            except Exception:
+                pass
+
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            c = cpu_reference(args.workload, args.cpu_frames, P=args.P)
+            m = statistics.median(c["ms"])
+            cpu = {"value": 1e3 / m, "unit": "frames/s", "cores": c["threads"], "kind": "port",
+                   "sample": "%d full %s frame(s) of the CPU oracle, median %.0f ms" % (len(c["ms"]), args.workload, m),
+                   "stage_ms": {k: v * 1e3 for k, v in c["stage"].items()}}
+
+        total_frames = K * world
+        line = {
+            "metric": METRIC, "value": total_frames / (dev_ms / 1e3), "unit": "frames/s", "n_gpus": world, "steps": K,
+            "warmup": Wm, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload], "name": args.workload, "P": sc.P, "width": W,
+                       "height": H, "sh_degree": sc.sh_degree, "num_rendered": R, "visible_gaussians": P_vis,
+                       "views_per_step": world, "parallelism": "views sharded, scene replicated" if world > 1 else "1 GPU",
+                       "l2": "no flush: the per-frame working set (%.2f GB attributes + scratch) exceeds the 126 MB L2"
+                             % ((sc.P * 236 + sc.P * 80 + R * 24) / 1e9),
+                       "blend": "simple" if args.simple_blend else "culled", "scene_upload_s": upload_s},
+            "e2e": {"value": total_frames / (e2e_ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": 144,
+                    "d2h_bytes_per_step": frame_bytes, "ms_per_step": e2e_ms / K, "checksum": checksum},
+            "gpu_launches": launches_per_frame * K * 1,
+            "clocks": clocks, "roofline": roof, "stages": stages,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        if gather_ms is not None:
+            line["gather"] = {"value": total_frames / (gather_ms / 1e3), "unit": "frames/s",
+                              "note": "render + NCCL gather of fp32 frames to rank 0"}
+        print(json.dumps(line))
+    vr.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,263 @@
+// blend.cu — per-16x16-tile front-to-back alpha blending (sm_100a).
+//
+// Replaces renderCUDA / render (/root/reference/apps/gsrast/gscuda/GSCuda.cu:543-693).
+// Semantics kept exactly: splats of a tile are visited in sorted order; a splat is skipped
+// when power > 0 or alpha = min(0.99, opacity*exp(power)) < 1/255; a pixel stops (and does
+// not blend the splat) when T*(1-alpha) < t_min; out = C + T*background; final_T and
+// n_contrib (1-based index of the last blended splat) are recorded per pixel.
+//
+// Two kernels:
+//   blend_simple_kernel  the reference's structure (256-splat shared-memory batches, one
+//                        pixel per thread) with the block-wide early exit; kept for A/B.
+//   blend_culled_kernel  default.  Each warp owns an 8x4-pixel sub-rectangle of the tile.
+//                        While a batch is staged, the staging thread of every splat computes
+//                        exactly-conservatively which of the 8 sub-rectangles the splat can
+//                        reach with alpha >= 1/255 (maximum of the concave quadratic `power`
+//                        over the rectangle); each warp then walks only its own survivors,
+//                        found with warp ballots, and leaves the batch loop as soon as its 32
+//                        pixels have saturated (__all_sync), independently of the other warps.
+// There is no dense contraction here, hence no tensor cores: the work is FP32 FMA + MUFU.EX2
+// issue and shared-memory broadcast bandwidth.
+#include "gsr_common.cuh"
+
+namespace gsr {
+
+namespace {
+
+constexpr int BLEND_THREADS = TILE_X * TILE_Y;  // 256
+constexpr int BATCH = 256;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float ALPHA_MIN = 1.0f / 255.0f;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLEND_THREADS) blend_simple_kernel(const BlendParams p) {
+    __shared__ float4 s_a[BATCH];  // x, y, conic.x, conic.y
+    __shared__ float4 s_b[BATCH];  // conic.z, opacity, r, g
+    __shared__ float s_c[BATCH];   // b
+
+    const int tile = blockIdx.x;
+    const int tile_x = tile % p.grid_x, tile_y = tile / p.grid_x;
+    const int tid = threadIdx.x;
+    const int lx = tid & 15, ly = tid >> 4;
+    const int pix_x = tile_x * TILE_X + lx, pix_y = tile_y * TILE_Y + ly;
+    const bool inside = pix_x < p.W && pix_y < p.H;
+    const float pixf_x = (float)pix_x, pixf_y = (float)pix_y;
+
+    const uint2 range = reinterpret_cast<const uint2*>(p.ranges)[tile];
+    const int total = (int)(range.y - range.x);
+    const int rounds = (total + BATCH - 1) / BATCH;
+    int todo = total;
+
+    bool done = !inside;
+    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+    uint32_t contributor = 0, last = 0;
+
+    for (int r = 0; r < rounds; ++r, todo -= BATCH) {
+        if (__syncthreads_count(done) == BLEND_THREADS) break;
+        const int progress = r * BATCH + tid;
+        if (progress < total) {
+            const uint32_t id = __ldg(p.point_list + range.x + progress);
+            const float2 xy = __ldg(reinterpret_cast<const float2*>(p.means2D) + id);
+            const float4 co = __ldg(reinterpret_cast<const float4*>(p.conic_opacity) + id);
+            const float* col = p.colors + (size_t)id * 3;
+            s_a[tid] = make_float4(xy.x, xy.y, co.x, co.y);
+            s_b[tid] = make_float4(co.z, co.w, __ldg(col), __ldg(col + 1));
+            s_c[tid] = __ldg(col + 2);
+        }
+        __syncthreads();
+        const int nb = min(BATCH, todo);
+        for (int j = 0; !done && j < nb; ++j) {
+            contributor++;
+            const float4 a = s_a[j];
+            const float4 b = s_b[j];
+            const float dx = a.x - pixf_x, dy = a.y - pixf_y;
+            const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
+            if (power > 0.0f) continue;
+            const float alpha = fminf(0.99f, b.y * __expf(power));
+            if (alpha < ALPHA_MIN) continue;
+            const float test_T = T * (1.0f - alpha);
+            if (test_T < p.t_min) {
+                done = true;
+                continue;
+            }
+            const float w = alpha * T;
+            C0 += b.z * w;
+            C1 += b.w * w;
+            C2 += s_c[j] * w;
+            T = test_T;
+            last = contributor;
+        }
+    }
+    if (inside) {
+        const size_t pix = (size_t)pix_y * p.W + pix_x;
+        const size_t plane = (size_t)p.W * p.H;
+        p.final_T[pix] = T;
+        p.n_contrib[pix] = last;
+        p.out_color[pix] = C0 + T * __ldg(p.background + 0);
+        p.out_color[pix + plane] = C1 + T * __ldg(p.background + 1);
+        p.out_color[pix + 2 * plane] = C2 + T * __ldg(p.background + 2);
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// Maximum of power(d) = -0.5*(a dx^2 + c dy^2) - b dx dy over the box dx in [x0,x1], dy in
+// [y0,y1] for a positive-definite conic: it is 0 when the box contains the origin, otherwise it
+// sits on the box edge nearest the origin along x or along y, at the 1-D optimum clamped to the
+// edge.  mba = -b/a, mbc = -b/c.
+__device__ __forceinline__ float max_power_in_box(float a, float b, float c, float mba, float mbc, float x0, float x1,
+                                                  float y0, float y1) {
+    const float ex = fminf(fmaxf(0.f, x0), x1);
+    const float ey = fminf(fmaxf(0.f, y0), y1);
+    const float dy1 = fminf(fmaxf(mbc * ex, y0), y1);
+    const float dx2 = fminf(fmaxf(mba * ey, x0), x1);
+    const float f1 = -0.5f * (a * ex * ex + c * dy1 * dy1) - b * ex * dy1;
+    const float f2 = -0.5f * (a * dx2 * dx2 + c * ey * ey) - b * dx2 * ey;
+    return fmaxf(f1, f2);
+}
+
+__global__ void __launch_bounds__(BLEND_THREADS) blend_culled_kernel(const BlendParams p) {
+    __shared__ float4 s_a[BATCH];      // x, y, a', b'      (conic pre-scaled by log2(e): see below)
+    __shared__ float4 s_b[BATCH];      // c', opacity, r, g
+    __shared__ float s_c[BATCH];       // b
+    __shared__ uint32_t s_mask[BATCH]; // bit w: splat can reach warp w's 8x4 sub-rectangle
+
+    const int tile = p.tile_order ? (int)__ldg(p.tile_order + blockIdx.x) : (int)blockIdx.x;
+    const int tile_x = tile % p.grid_x, tile_y = tile / p.grid_x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // warp w -> sub-rectangle (w&1, w>>1) of 8x4 pixels; lane -> (lane&7, lane>>3)
+    const int lx = ((warp & 1) << 3) | (lane & 7), ly = ((warp >> 1) << 2) | (lane >> 3);
+    const int pix_x = tile_x * TILE_X + lx, pix_y = tile_y * TILE_Y + ly;
+    const bool inside = pix_x < p.W && pix_y < p.H;
+    const float pixf_x = (float)pix_x, pixf_y = (float)pix_y;
+    const float tile_x0 = (float)(tile_x * TILE_X), tile_y0 = (float)(tile_y * TILE_Y);
+
+    const uint2 range = reinterpret_cast<const uint2*>(p.ranges)[tile];
+    const int total = (int)(range.y - range.x);
+    const int rounds = (total + BATCH - 1) / BATCH;
+
+    bool done = !inside;
+    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+    uint32_t last = 0;
+    bool warp_done = __all_sync(0xffffffffu, done);
+
+    for (int r = 0; r < rounds; ++r) {
+        if (__syncthreads_and(warp_done)) break;
+        const int progress = r * BATCH + tid;
+        uint32_t m = 0;
+        if (progress < total) {
+            const uint32_t id = __ldg(p.point_list + range.x + progress);
+            const float2 xy = __ldg(reinterpret_cast<const float2*>(p.means2D) + id);
+            const float4 co = __ldg(reinterpret_cast<const float4*>(p.conic_opacity) + id);
+            const float* col = p.colors + (size_t)id * 3;
+            const float a = co.x, b = co.y, c = co.z, o = co.w;
+            // power*log2(e) = a' dx^2 + c' dy^2 + b' dx dy  with a' = -0.5 a log2e, ...
+            s_a[tid] = make_float4(xy.x, xy.y, -0.5f * LOG2E * a, -LOG2E * b);
+            s_b[tid] = make_float4(-0.5f * LOG2E * c, o, __ldg(col), __ldg(col + 1));
+            s_c[tid] = __ldg(col + 2);
+            // ---- which sub-rectangles can see this splat with alpha >= 1/255 ? ----------
+            // alpha >= 1/255  <=>  power >= -ln(255*o).  Keep a small slack so float rounding in
+            // the bound can only add work, never drop a contributing splat.
+            const float det = a * c - b * b;
+            if (!(o >= ALPHA_MIN * 0.999f)) {
+                m = 0;  // exp(power) <= 1  =>  alpha < 1/255 everywhere (also catches NaN opacity)
+            } else if (!(a > 0.f && c > 0.f && det > 0.f) || !(fabsf(xy.x) < 1e7f) || !(fabsf(xy.y) < 1e7f)) {
+                m = 0xffu;  // degenerate conic: no culling
+            } else {
+                const float thr = -__logf(255.0f * o) * 1.0001f - 1e-3f;
+                const float mba = -b / a, mbc = -b / c;
+                // dx = x - px, px in [X, X+w-1]  ->  dx in [x - (X+w-1), x - X]
+                const float bx1 = xy.x - tile_x0, by1 = xy.y - tile_y0;
+                if (max_power_in_box(a, b, c, mba, mbc, bx1 - 15.f, bx1, by1 - 15.f, by1) >= thr) {
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) {
+                        const float wx1 = bx1 - (float)((w & 1) << 3), wy1 = by1 - (float)((w >> 1) << 2);
+                        if (max_power_in_box(a, b, c, mba, mbc, wx1 - 7.f, wx1, wy1 - 3.f, wy1) >= thr) m |= 1u << w;
+                    }
+                }
+            }
+        }
+        s_mask[tid] = m;
+        __syncthreads();
+
+        if (!warp_done) {
+            const int nb = min(BATCH, total - r * BATCH);
+            for (int c0 = 0; c0 < nb; c0 += 32) {
+                unsigned bits = __ballot_sync(0xffffffffu, (s_mask[c0 + lane] >> warp) & 1u);
+                while (bits) {
+                    const int j = c0 + __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const float4 a = s_a[j];
+                    const float4 b = s_b[j];
+                    const float dx = a.x - pixf_x, dy = a.y - pixf_y;
+                    const float p2 = fmaf(a.z, dx * dx, fmaf(b.x, dy * dy, a.w * (dx * dy)));
+                    const float alpha = fminf(0.99f, b.y * ex2_approx(p2));
+                    if (done || p2 > 0.0f || alpha < ALPHA_MIN) continue;
+                    const float test_T = T * (1.0f - alpha);
+                    if (test_T < p.t_min) {
+                        done = true;
+                        continue;
+                    }
+                    const float w = alpha * T;
+                    C0 = fmaf(b.z, w, C0);
+                    C1 = fmaf(b.w, w, C1);
+                    C2 = fmaf(s_c[j], w, C2);
+                    T = test_T;
+                    last = (uint32_t)(r * BATCH + j + 1);
+                }
+                if (__all_sync(0xffffffffu, done)) {
+                    warp_done = true;
+                    break;
+                }
+            }
+        }
+    }
+    if (inside) {
+        const size_t pix = (size_t)pix_y * p.W + pix_x;
+        const size_t plane = (size_t)p.W * p.H;
+        p.final_T[pix] = T;
+        p.n_contrib[pix] = last;
+        p.out_color[pix] = fmaf(T, __ldg(p.background + 0), C0);
+        p.out_color[pix + plane] = fmaf(T, __ldg(p.background + 1), C1);
+        p.out_color[pix + 2 * plane] = fmaf(T, __ldg(p.background + 2), C2);
+    }
+}
+
+__global__ void fill_background_kernel(int n, const float* __restrict__ background, float* __restrict__ out_color,
+                                       float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    final_T[i] = 1.0f;
+    n_contrib[i] = 0;
+    out_color[i] = background[0];
+    out_color[i + (size_t)n] = background[1];
+    out_color[i + 2 * (size_t)n] = background[2];
+}
+
+}  // namespace
+
+int launch_blend(const BlendParams& p, bool simple, cudaStream_t s) {
+    const int tiles = p.grid_x * p.grid_y;
+    if (tiles <= 0) return 0;
+    if (simple)
+        blend_simple_kernel<<<tiles, BLEND_THREADS, 0, s>>>(p);
+    else
+        blend_culled_kernel<<<tiles, BLEND_THREADS, 0, s>>>(p);
+    cudaError_t e = cudaPeekAtLastError();
+    return e == cudaSuccess ? 1 : -(int)e;
+}
+
+int launch_fill_background(int W, int H, const float* background, float* out_color, float* final_T,
+                           uint32_t* n_contrib, cudaStream_t s) {
+    const int n = W * H;
+    fill_background_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, background, out_color, final_T, n_contrib);
+    cudaError_t e = cudaPeekAtLastError();
+    return e == cudaSuccess ? 1 : -(int)e;
+}
+
+}  // namespace gsr

@@ -1,0 +1,425 @@
+// forward.cu — host orchestration + C ABI of the forward rasterizer.
+//
+// Replaces gscuda::forward (/root/reference/apps/gsrast/gscuda/GSCuda.cu:695-811) and the
+// scratch-buffer carving of AuxBuffer.cu:13-89 / AuxBuffer.cuh:8-14.  Stage order and the
+// allocator protocol are the reference's: geometry chunk -> image chunk -> preprocess -> scan
+// -> (num_rendered to the host) -> binning chunk -> duplicate -> sort -> ranges -> blend.
+// Differences that are deliberate:
+//   * the only host<->device round trip is the 4-byte num_rendered, written by the scan
+//     kernel straight into mapped pinned memory (the reference does a blocking cudaMemcpy,
+//     GSCuda.cu:772, and its caller a cudaDeviceSynchronize per call, CudaBuffer.hpp:8-12);
+//   * `ranges` is one entry per tile, not per pixel (GSCuda.cu:800 clears W*H entries);
+//   * everything runs on the caller's stream.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+
+#include "gsr_common.cuh"
+
+namespace gsr {
+
+namespace {
+
+// obtain() of AuxBuffer.cu:13-21: bump allocation at 128-byte alignment.
+template <typename T>
+void obtain(char*& chunk, T*& out, size_t bytes, size_t align = 128) {
+    size_t off = reinterpret_cast<size_t>(chunk);
+    size_t aligned = (off + align - 1) / align * align;
+    out = reinterpret_cast<T*>(aligned);
+    chunk = reinterpret_cast<char*>(aligned + bytes);
+}
+
+int num_pre_blocks(int P) { return (P + PRE_THREADS - 1) / PRE_THREADS; }
+
+// Mapped pinned slot for the num_rendered readback, one per host thread and device.
+thread_local HostSlot g_slot;
+
+}  // namespace
+
+int ensure_slot(HostSlot& s) {
+    int dev = 0;
+    GSR_CUDA_TRY(cudaGetDevice(&dev));
+    if (s.host && s.device == dev) return 0;
+    if (s.host) cudaFreeHost(s.host);
+    s.host = nullptr;
+    void* h = nullptr;
+    GSR_CUDA_TRY(cudaHostAlloc(&h, 64, cudaHostAllocMapped));
+    s.host = static_cast<uint32_t*>(h);
+    void* d = nullptr;
+    GSR_CUDA_TRY(cudaHostGetDevicePointer(&d, h, 0));
+    s.dev = static_cast<uint32_t*>(d);
+    s.device = dev;
+    return 0;
+}
+
+void release_slot(HostSlot& s) {
+    if (s.host) cudaFreeHost(s.host);
+    s.host = s.dev = nullptr;
+    s.device = -1;
+}
+
+namespace {
+
+struct StageTimer {
+    bool on = false;
+    cudaStream_t s = nullptr;
+    cudaEvent_t ev[8];
+    int n = 0;
+    int init(bool enable, cudaStream_t stream) {
+        on = enable;
+        s = stream;
+        if (!on) return 0;
+        for (auto& e : ev) GSR_CUDA_TRY(cudaEventCreate(&e));
+        return 0;
+    }
+    void mark() {
+        if (on && n < 8) cudaEventRecord(ev[n++], s);
+    }
+    float ms(int a, int b) {
+        float t = 0.f;
+        if (on && a < n && b < n) cudaEventElapsedTime(&t, ev[a], ev[b]);
+        return t;
+    }
+    void destroy() {
+        if (on)
+            for (auto& e : ev) cudaEventDestroy(e);
+        on = false;
+    }
+};
+
+}  // namespace
+
+}  // namespace gsr
+
+using namespace gsr;
+
+extern "C" {
+
+uint32_t gsr_get_higher_msb(uint32_t n) {
+    // GSCuda.cu:481-502: binary search for the position above the highest set bit
+    uint32_t msb = sizeof(n) * 4;
+    uint32_t step = msb;
+    while (step > 1) {
+        step /= 2;
+        if (n >> msb) msb += step;
+        else msb -= step;
+    }
+    if (n >> msb) msb++;
+    return msb;
+}
+
+size_t gsr_geometry_state_map(char* chunk, int P, gsr_geometry_state* g) {
+    char* c = chunk;
+    const size_t n = (size_t)(P > 0 ? P : 0);
+    gsr_geometry_state st;
+    obtain(c, st.depths, n * sizeof(float));
+    obtain(c, st.clamped, n * 3);
+    obtain(c, st.internal_radii, n * sizeof(int));
+    obtain(c, st.means2D, n * 2 * sizeof(float));
+    obtain(c, st.cov3D, n * 6 * sizeof(float));
+    obtain(c, st.conic_opacity, n * 4 * sizeof(float));
+    obtain(c, st.rgb, n * 3 * sizeof(float));
+    obtain(c, st.tiles_touched, n * sizeof(uint32_t));
+    st.scan_size = ((size_t)num_pre_blocks(P) + 4) * sizeof(uint32_t);
+    obtain(c, st.block_sums, st.scan_size);
+    obtain(c, st.point_offsets, n * sizeof(uint32_t));
+    if (g) *g = st;
+    return (size_t)(c - chunk);
+}
+
+size_t gsr_image_state_map(char* chunk, int width, int height, gsr_image_state* im) {
+    char* c = chunk;
+    const size_t N = (size_t)width * (size_t)height;
+    const size_t T = (size_t)((width + TILE_X - 1) / TILE_X) * (size_t)((height + TILE_Y - 1) / TILE_Y);
+    gsr_image_state st;
+    obtain(c, st.ranges, T * 2 * sizeof(uint32_t));
+    obtain(c, st.n_contrib, N * sizeof(uint32_t));
+    obtain(c, st.accum_alpha, N * sizeof(float));
+    obtain(c, st.tile_order, T * sizeof(uint32_t));
+    if (im) *im = st;
+    return (size_t)(c - chunk);
+}
+
+size_t gsr_binning_state_map(char* chunk, size_t R, gsr_binning_state* b) {
+    char* c = chunk;
+    gsr_binning_state st;
+    obtain(c, st.point_list_keys_unsorted, R * sizeof(uint64_t));
+    obtain(c, st.point_list_keys, R * sizeof(uint64_t));
+    obtain(c, st.point_list_unsorted, R * sizeof(uint32_t));
+    obtain(c, st.point_list, R * sizeof(uint32_t));
+    st.sorting_size = sort_temp_bytes(R);
+    obtain(c, st.list_sorting_space, st.sorting_size);
+    if (b) *b = st;
+    return (size_t)(c - chunk);
+}
+
+// required<T>() probes with a null chunk; +128 covers a chunk base that is not 128-aligned
+// (the reference over-asks the same way, GSCuda.cu:735,783).
+size_t gsr_geometry_state_required(int P) { return gsr_geometry_state_map(nullptr, P, nullptr) + 128; }
+size_t gsr_image_state_required(int width, int height) { return gsr_image_state_map(nullptr, width, height, nullptr) + 128; }
+size_t gsr_binning_state_required(size_t R) { return gsr_binning_state_map(nullptr, R, nullptr) + 128; }
+
+int gsr_forward_ex(const gsr_forward_args* a) { return gsr::forward_impl(a, nullptr); }
+
+}  // extern "C"
+
+int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
+    HostSlot& slot = slot_in ? *slot_in : g_slot;
+    if (!a || !a->geometry_alloc || !a->binning_alloc || !a->image_alloc) return GSR_ERR_INVALID_ARG;
+    if (a->P < 0 || a->width <= 0 || a->height <= 0 || !a->out_color || !a->background) return GSR_ERR_INVALID_ARG;
+    if (a->P > 0 && (!a->means3D || !a->opacities || !a->viewmatrix || !a->projmatrix)) return GSR_ERR_INVALID_ARG;
+    if (a->P > 0 && !a->cov3D_precomp && (!a->scales || !a->rotations)) return GSR_ERR_INVALID_ARG;
+    if (a->P > 0 && !a->colors_precomp && !a->shs) return GSR_ERR_INVALID_ARG;
+    const bool compat = (a->flags & GSR_FLAG_GSRAST_COMPAT) != 0;
+    if (a->P > 0 && !compat && !a->colors_precomp && !a->cam_pos) return GSR_ERR_INVALID_ARG;
+    const int ms = a->means_stride ? a->means_stride : 3, ss = a->scales_stride ? a->scales_stride : 3;
+    if ((ms != 3 && ms != 4) || (ss != 3 && ss != 4)) return GSR_ERR_INVALID_ARG;
+    if (!compat && !a->colors_precomp && (a->D < 0 || a->D > 3 || a->M < 1)) return GSR_ERR_INVALID_ARG;
+
+    cudaStream_t s = static_cast<cudaStream_t>(a->stream);
+    const int P = a->P, W = a->width, H = a->height;
+    const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
+    const int tiles = gx * gy;
+    int launches = 0, rc = 0;
+
+    StageTimer tm;
+    if ((rc = tm.init(a->timings != nullptr, s)) < 0) return rc;
+#define GSR_STAGE(call)               \
+    do {                              \
+        rc = (call);                  \
+        if (rc < 0) {                 \
+            tm.destroy();             \
+            return rc;                \
+        }                             \
+        launches += rc;               \
+    } while (0)
+
+    // geometry chunk (GSCuda.cu:723-729)
+    char* gchunk = a->geometry_alloc(gsr_geometry_state_required(P), a->geometry_user);
+    if (!gchunk) { tm.destroy(); return GSR_ERR_ALLOC_FAILED; }
+    gsr_geometry_state geom;
+    gsr_geometry_state_map(gchunk, P, &geom);
+    int* radii = a->radii ? a->radii : geom.internal_radii;
+
+    // image chunk (GSCuda.cu:734-736)
+    char* ichunk = a->image_alloc(gsr_image_state_required(W, H), a->image_user);
+    if (!ichunk) { tm.destroy(); return GSR_ERR_ALLOC_FAILED; }
+    gsr_image_state img;
+    gsr_image_state_map(ichunk, W, H, &img);
+
+    uint32_t R = 0;
+    tm.mark();  // 0
+    if (P > 0) {
+        if ((rc = ensure_slot(slot)) < 0) { tm.destroy(); return rc; }
+        PreprocessParams pp;
+        memset(&pp, 0, sizeof(pp));
+        pp.P = P; pp.D = a->D; pp.M = a->M; pp.W = W; pp.H = H; pp.grid_x = gx; pp.grid_y = gy;
+        pp.means3D = a->means3D; pp.means_stride = ms;
+        pp.scales = a->scales; pp.scales_stride = ss;
+        pp.rotations = a->rotations; pp.opacities = a->opacities; pp.shs = a->shs;
+        pp.colors_precomp = a->colors_precomp; pp.cov3D_precomp = a->cov3D_precomp;
+        pp.viewmatrix = a->viewmatrix; pp.projmatrix = a->projmatrix; pp.cam_pos = a->cam_pos;
+        pp.scale_modifier = a->scale_modifier;
+        pp.tan_fovx = a->tan_fovx; pp.tan_fovy = a->tan_fovy;
+        pp.focal_y = (float)H / (2.0f * a->tan_fovy);  // GSCuda.cu:721
+        pp.focal_x = (float)W / (2.0f * a->tan_fovx);
+        const float fm = std::numeric_limits<float>::max();  // GSCuda.cu:738-741
+        for (int i = 0; i < 3; ++i) {
+            pp.boxmin[i] = a->boxmin ? a->boxmin[i] : -fm;
+            pp.boxmax[i] = a->boxmax ? a->boxmax[i] : fm;
+        }
+        pp.prefiltered = a->prefiltered;
+        pp.radii = radii; pp.rects = a->rects; pp.depths = geom.depths; pp.clamped = geom.clamped;
+        pp.means2D = geom.means2D; pp.cov3D = geom.cov3D; pp.conic_opacity = geom.conic_opacity;
+        pp.rgb = geom.rgb; pp.tiles_touched = geom.tiles_touched; pp.block_sums = geom.block_sums;
+        GSR_STAGE(launch_preprocess(pp, compat, s));
+        tm.mark();  // 1
+        const int nb = num_pre_blocks(P);
+        GSR_STAGE(launch_scan_block_sums(geom.block_sums, nb, geom.block_sums + nb, slot.dev, s));
+        tm.mark();  // 2
+        // the one host round trip: num_rendered decides the binning allocation (GSCuda.cu:772,782)
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { tm.destroy(); return -(int)e; }
+        R = *static_cast<volatile uint32_t*>(slot.host);
+    } else {
+        tm.mark();
+        tm.mark();
+    }
+
+    if (R == 0) {
+        // GSCuda.cu:775-778 returns here leaving out_color stale; the contract renders background.
+        if (!compat) GSR_STAGE(launch_fill_background(W, H, a->background, a->out_color, img.accum_alpha, img.n_contrib, s));
+        if (a->timings) {
+            cudaStreamSynchronize(s);
+            memset(a->timings, 0, sizeof(*a->timings));
+            a->timings->preprocess_ms = tm.ms(0, 1);
+            a->timings->scan_ms = tm.ms(1, 2);
+            a->timings->total_ms = tm.ms(0, 2);
+            a->timings->kernel_launches = launches;
+        }
+        tm.destroy();
+        return 0;
+    }
+    if (R >= (1u << 30)) { tm.destroy(); return GSR_ERR_TOO_MANY_PAIRS; }
+
+    // binning chunk (GSCuda.cu:782-784)
+    char* bchunk = a->binning_alloc(gsr_binning_state_required(R), a->binning_user);
+    if (!bchunk) { tm.destroy(); return GSR_ERR_ALLOC_FAILED; }
+    gsr_binning_state bin;
+    gsr_binning_state_map(bchunk, R, &bin);
+
+    const int end_bit = 32 + (int)gsr_get_higher_msb((uint32_t)tiles);  // GSCuda.cu:791-797
+    const int passes = sort_num_passes(end_bit);
+    // Ping-pong start buffer chosen so the sorted lists land in point_list_keys / point_list.
+    const bool start_in_sorted = (passes % 2) == 0;
+    uint64_t* ka = start_in_sorted ? bin.point_list_keys : bin.point_list_keys_unsorted;
+    uint32_t* va = start_in_sorted ? bin.point_list : bin.point_list_unsorted;
+    uint64_t* kb = start_in_sorted ? bin.point_list_keys_unsorted : bin.point_list_keys;
+    uint32_t* vb = start_in_sorted ? bin.point_list_unsorted : bin.point_list;
+
+    GSR_STAGE(launch_duplicate(P, gx, gy, geom.means2D, geom.depths, geom.tiles_touched, geom.block_sums, radii,
+                               a->rects, geom.point_offsets, ka, va, s));
+    tm.mark();  // 3
+    bool in_a = false;
+    cudaEvent_t sort_ev[10];
+    const bool sort_timed = tm.on;
+    if (sort_timed)
+        for (auto& e : sort_ev) cudaEventCreate(&e);
+    rc = launch_sort_pairs(ka, va, kb, vb, R, end_bit, bin.list_sorting_space, &in_a, s, sort_timed ? sort_ev : nullptr);
+    if (rc < 0) {
+        if (sort_timed)
+            for (auto& e : sort_ev) cudaEventDestroy(e);
+        tm.destroy();
+        return rc;
+    }
+    launches += rc;
+    tm.mark();  // 4
+    GSR_STAGE(launch_identify_ranges(bin.point_list_keys, R, img.ranges, tiles, compat, s));
+    tm.mark();  // 5
+
+    BlendParams bp;
+    memset(&bp, 0, sizeof(bp));
+    bp.W = W; bp.H = H; bp.grid_x = gx; bp.grid_y = gy;
+    bp.ranges = img.ranges; bp.point_list = bin.point_list; bp.means2D = geom.means2D;
+    bp.colors = a->colors_precomp ? a->colors_precomp : geom.rgb;  // GSCuda.cu:803
+    bp.conic_opacity = geom.conic_opacity; bp.background = a->background;
+    bp.final_T = img.accum_alpha; bp.n_contrib = img.n_contrib; bp.out_color = a->out_color;
+    bp.t_min = compat ? 0.001f : 0.0001f;  // GSCuda.cu:653 vs contract
+    bp.tile_order = nullptr;
+    GSR_STAGE(launch_blend(bp, (a->flags & GSR_FLAG_BLEND_SIMPLE) != 0, s));
+    tm.mark();  // 6
+#undef GSR_STAGE
+
+    if (a->timings) {
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { tm.destroy(); return -(int)e; }
+        gsr_stage_times* t = a->timings;
+        t->preprocess_ms = tm.ms(0, 1);
+        t->scan_ms = tm.ms(1, 2);
+        t->duplicate_ms = tm.ms(2, 3);
+        t->sort_ms = tm.ms(3, 4);
+        t->ranges_ms = tm.ms(4, 5);
+        t->blend_ms = tm.ms(5, 6);
+        t->total_ms = tm.ms(0, 6);
+        t->num_rendered = (int)R;
+        t->sort_passes = passes;
+        t->kernel_launches = launches;
+        t->sort_hist_ms = 0.f;
+        for (int i = 0; i < 8; ++i) t->sort_pass_ms[i] = 0.f;
+        cudaEventElapsedTime(&t->sort_hist_ms, sort_ev[0], sort_ev[1]);
+        for (int i = 0; i < passes && i < 8; ++i) cudaEventElapsedTime(&t->sort_pass_ms[i], sort_ev[1 + i], sort_ev[2 + i]);
+    }
+    if (sort_timed)
+        for (auto& e : sort_ev) cudaEventDestroy(e);
+    tm.destroy();
+    return (int)R;
+}
+
+extern "C" {
+
+static void fill_args(gsr_forward_args& x, gsr_alloc_fn ga, void* gu, gsr_alloc_fn ba, void* bu, gsr_alloc_fn ia,
+                      void* iu, int P, int D, int M, const float* background, int width, int height,
+                      const float* means3D, const float* shs, const float* colors_precomp, const float* opacities,
+                      const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                      const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
+                      float tan_fovy, int prefiltered, float* out_color, int* radii, int* rects, const float* boxmin,
+                      const float* boxmax, void* stream) {
+    memset(&x, 0, sizeof(x));
+    x.geometry_alloc = ga; x.geometry_user = gu; x.binning_alloc = ba; x.binning_user = bu;
+    x.image_alloc = ia; x.image_user = iu;
+    x.P = P; x.D = D; x.M = M; x.background = background; x.width = width; x.height = height;
+    x.means3D = means3D; x.shs = shs; x.colors_precomp = colors_precomp; x.opacities = opacities;
+    x.scales = scales; x.scale_modifier = scale_modifier; x.rotations = rotations;
+    x.cov3D_precomp = cov3D_precomp; x.viewmatrix = viewmatrix; x.projmatrix = projmatrix; x.cam_pos = cam_pos;
+    x.tan_fovx = tan_fovx; x.tan_fovy = tan_fovy; x.prefiltered = prefiltered; x.out_color = out_color;
+    x.radii = radii; x.rects = rects; x.boxmin = boxmin; x.boxmax = boxmax; x.stream = stream;
+}
+
+int gsr_forward(gsr_alloc_fn ga, void* gu, gsr_alloc_fn ba, void* bu, gsr_alloc_fn ia, void* iu, int P, int D, int M,
+                const float* background, int width, int height, const float* means3D, const float* shs,
+                const float* colors_precomp, const float* opacities, const float* scales, float scale_modifier,
+                const float* rotations, const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+                const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered, float* out_color, int* radii,
+                int* rects, const float* boxmin, const float* boxmax, void* stream) {
+    gsr_forward_args x;
+    fill_args(x, ga, gu, ba, bu, ia, iu, P, D, M, background, width, height, means3D, shs, colors_precomp, opacities,
+              scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy,
+              prefiltered, out_color, radii, rects, boxmin, boxmax, stream);
+    x.means_stride = 3;
+    x.scales_stride = 3;
+    return gsr_forward_ex(&x);
+}
+
+int gsr_forward_gscuda(gsr_alloc_fn ga, void* gu, gsr_alloc_fn ba, void* bu, gsr_alloc_fn ia, void* iu, int P, int D,
+                       int M, const float* background, int width, int height, const float* means3D, const float* shs,
+                       const float* colors_precomp, const float* opacities, const float* scales,
+                       float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                       const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
+                       float tan_fovy, int prefiltered, float* out_color, int* radii, int* rects, const float* boxmin,
+                       const float* boxmax, void* stream) {
+    gsr_forward_args x;
+    fill_args(x, ga, gu, ba, bu, ia, iu, P, D, M, background, width, height, means3D, shs, colors_precomp, opacities,
+              scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy,
+              prefiltered, out_color, radii, rects, boxmin, boxmax, stream);
+    x.means_stride = 4;  // GSGaussians.cpp:121-125: vec4 positions and scales
+    x.scales_stride = 4;
+    x.flags = GSR_FLAG_GSRAST_COMPAT;
+    return gsr_forward_ex(&x);
+}
+
+size_t gsr_sort_pairs_temp_bytes(size_t n) { return sort_temp_bytes(n); }
+
+int gsr_sort_pairs(uint64_t* keys_in, uint32_t* vals_in, uint64_t* keys_out, uint32_t* vals_out, size_t n, int end_bit,
+                   char* temp, void* stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    bool in_a = false;
+    int rc = launch_sort_pairs(keys_in, vals_in, keys_out, vals_out, n, end_bit, temp, &in_a, s);
+    if (rc < 0) return rc;
+    if (in_a && n > 0) {
+        GSR_CUDA_TRY(cudaMemcpyAsync(keys_out, keys_in, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+        GSR_CUDA_TRY(cudaMemcpyAsync(vals_out, vals_in, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    }
+    return rc;
+}
+
+int gsr_identify_tile_ranges(const uint64_t* sorted_keys, size_t n, uint32_t* ranges, int num_tiles, unsigned flags,
+                             void* stream) {
+    return launch_identify_ranges(sorted_keys, n, ranges, num_tiles, (flags & GSR_FLAG_GSRAST_COMPAT) != 0,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+const char* gsr_error_string(int code) {
+    if (code >= 0) return "success";
+    switch (code) {
+        case GSR_ERR_INVALID_ARG: return "gsrast_b200: invalid argument";
+        case GSR_ERR_ALLOC_FAILED: return "gsrast_b200: scratch allocator returned NULL";
+        case GSR_ERR_TOO_MANY_PAIRS: return "gsrast_b200: num_rendered >= 2^30";
+        case GSR_ERR_SORT_STALLED: return "gsrast_b200: radix sort look-back watchdog tripped";
+        default: return cudaGetErrorString(static_cast<cudaError_t>(-code));
+    }
+}
+
+int gsr_version(void) { return GSR_VERSION; }
+
+}  // extern "C"

@@ -1,0 +1,118 @@
+// gsr_common.cuh — shared declarations of the sm_100a splat forward rasterizer.
+// Internal; the public surface is include/gsrast_b200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gsrast_b200.h"
+
+namespace gsr {
+
+constexpr int TILE_X = 16;  // BLOCK_X / BLOCK_Y of the reference (GSCuda.cu:20-21, Config.hpp:47-48)
+constexpr int TILE_Y = 16;
+constexpr int PRE_THREADS = 256;  // Gaussians per preprocess / duplicate block
+
+// ---- individually rounded binary32 arithmetic ------------------------------------------
+// The integer outputs of preprocess (radii, tile rects, depth key bits) are defined by
+// IEEE operations in the source's association order; these intrinsics are never contracted
+// into FMAs by nvcc, so the kernel matches the CPU oracle bit for bit.
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ float frcp(float a) { return __frcp_rn(a); }
+// a*b + c*d + e*f, left to right (glm mat3 products, transformPoint)
+__device__ __forceinline__ float dot3(float a, float b, float c, float d, float e, float f) {
+    return fadd(fadd(fmul(a, b), fmul(c, d)), fmul(e, f));
+}
+
+struct PreprocessParams {
+    int P, D, M;
+    int W, H;
+    int grid_x, grid_y;
+    const float* means3D; int means_stride;
+    const float* scales;  int scales_stride;
+    const float* rotations;
+    const float* opacities;
+    const float* shs;
+    const float* colors_precomp;
+    const float* cov3D_precomp;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* cam_pos;
+    float scale_modifier;
+    float tan_fovx, tan_fovy;
+    float focal_x, focal_y;
+    float boxmin[3], boxmax[3];
+    int prefiltered;
+    // outputs
+    int* radii;
+    int* rects;  // int2[P] or null
+    float* depths;
+    unsigned char* clamped;
+    float* means2D;
+    float* cov3D;
+    float* conic_opacity;
+    float* rgb;
+    uint32_t* tiles_touched;
+    uint32_t* block_sums;  // [ceil(P/256)]
+};
+
+// stage launchers (each returns the number of kernels it launched, or <0 on error)
+int launch_preprocess(const PreprocessParams& p, bool compat, cudaStream_t s);
+int launch_scan_block_sums(uint32_t* block_sums, int num_blocks, uint32_t* total_dev, uint32_t* total_host_mapped,
+                           cudaStream_t s);
+int launch_duplicate(int P, int grid_x, int grid_y, const float* means2D, const float* depths,
+                     const uint32_t* tiles_touched, const uint32_t* block_sums, const int* radii, const int* rects,
+                     uint32_t* point_offsets, uint64_t* keys_out, uint32_t* vals_out, cudaStream_t s);
+int launch_identify_ranges(const uint64_t* keys, size_t n, uint32_t* ranges, int num_tiles, bool compat,
+                           cudaStream_t s);
+
+// radix sort
+size_t sort_temp_bytes(size_t n);
+int sort_num_passes(int end_bit);
+// Sorts over bits [0,end_bit). The result lands in (keys_b, vals_b) when the pass count is odd and in
+// (keys_a, vals_a) when it is even; `*result_in_a` says which.  The forward path picks its buffers so
+// that the sorted lists land in point_list_keys / point_list without a final copy.
+// `events` (optional, passes+2 entries) are recorded before the histogram, after it, and after every pass.
+int launch_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, size_t n, int end_bit,
+                      char* temp, bool* result_in_a, cudaStream_t s, cudaEvent_t* events = nullptr);
+
+struct BlendParams {
+    int W, H, grid_x, grid_y;
+    const uint32_t* ranges;      // uint2[tiles]
+    const uint32_t* point_list;  // sorted Gaussian ids
+    const float* means2D;
+    const float* colors;         // float3[P]
+    const float* conic_opacity;
+    const float* background;     // device float[3]
+    float* final_T;
+    uint32_t* n_contrib;
+    float* out_color;
+    float t_min;                 // 0.0001f contract, 0.001f GSRast
+    const uint32_t* tile_order;  // optional
+};
+int launch_blend(const BlendParams& p, bool simple, cudaStream_t s);
+int launch_fill_background(int W, int H, const float* background, float* out_color, float* final_T,
+                           uint32_t* n_contrib, cudaStream_t s);
+
+// Mapped pinned word that receives num_rendered (the pipeline's only host round trip).
+struct HostSlot {
+    uint32_t* host = nullptr;
+    uint32_t* dev = nullptr;
+    int device = -1;
+};
+int ensure_slot(HostSlot& s);
+void release_slot(HostSlot& s);
+// gsr_forward_ex with an explicit readback slot (nullptr = the calling thread's own).
+int forward_impl(const gsr_forward_args* args, HostSlot* slot);
+
+}  // namespace gsr
+
+#define GSR_CUDA_TRY(expr)                          \
+    do {                                            \
+        cudaError_t _e = (expr);                    \
+        if (_e != cudaSuccess) return -(int)_e;     \
+    } while (0)

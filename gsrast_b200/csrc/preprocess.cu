@@ -1,0 +1,465 @@
+// preprocess.cu — per-Gaussian stage of the forward rasterizer (sm_100a).
+//
+// Replaces preprocessCUDA / preprocess (apps/gsrast/gscuda/GSCuda.cu:261-415) together with
+// quatToMat / computeCov3D (:157-195), computeCov2D (:197-231) and getRect (:237-259), and
+// the per-block partial sums of the tiles_touched scan (cub::DeviceScan::InclusiveSum, :771).
+//
+// Two arithmetic modes, selected at compile time:
+//   COMPAT=false  CudaRasterizer contract: near-plane cull on view z,
+//                 un-normalised quaternion, focal_x/focal_y, ndc2Pix in double, view-space
+//                 depth, SH degree 0..3 with clamping.
+//   COMPAT=true   the in-tree gscuda semantics, restated operation by operation.
+//
+// HBM traffic: one pass over the attribute stream.  means/scales (float3 records) are
+// fetched as coalesced float4 and re-sliced through shared memory; rotations are float4
+// per thread; the 192-B SH block is only touched for Gaussians that survive culling, by
+// 4 lanes per Gaussian x 3 float4 each (each lane owns 4 coefficients x RGB), after a
+// warp-level compaction of the survivors.
+//
+// All arithmetic that feeds an integer output goes through the individually rounded
+// intrinsics of gsr_common.cuh so the results are bit-identical to oracle/gsr_oracle.cpp.
+#include "gsr_common.cuh"
+
+namespace gsr {
+
+namespace {
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// getRect (GSCuda.cu:237-259): tile-space AABB, truncation toward zero, clamped to the grid.
+__device__ __forceinline__ void get_rect(float px, float py, int ex, int ey, int gx, int gy, int& minx, int& miny,
+                                         int& maxx, int& maxy) {
+    minx = min(gx, max(0, __float2int_rz(fdiv(fsub(px, (float)ex), (float)TILE_X))));
+    miny = min(gy, max(0, __float2int_rz(fdiv(fsub(py, (float)ey), (float)TILE_Y))));
+    maxx = min(gx, max(0, __float2int_rz(fdiv(fsub(fadd(fadd(px, (float)ex), (float)TILE_X), 1.0f), (float)TILE_X))));
+    maxy = min(gy, max(0, __float2int_rz(fdiv(fsub(fadd(fadd(py, (float)ey), (float)TILE_Y), 1.0f), (float)TILE_Y))));
+}
+
+// upstream ndc2Pix: ((v + 1.0) * S - 1.0) * 0.5 evaluated in double, rounded to float once.
+__device__ __forceinline__ float ndc2pix(float v, int S) {
+    double t = __dadd_rn((double)v, 1.0);
+    t = __dmul_rn(t, (double)S);
+    t = __dadd_rn(t, -1.0);
+    t = __dmul_rn(t, 0.5);
+    return __double2float_rn(t);
+}
+
+__device__ __forceinline__ float glm_min(float a, float b) { return (b < a) ? b : a; }
+__device__ __forceinline__ float glm_max(float a, float b) { return (a < b) ? b : a; }
+
+// Sigma^T-projected 2D covariance; shared tail of both modes.
+// T0[r] = T.c[0][r], T1[r] = T.c[1][r]; c[] = packed symmetric cov3D.
+__device__ __forceinline__ void project_cov(const float T0[3], const float T1[3], const float c[6], float& cov00,
+                                            float& cov01, float& cov11) {
+    float A00 = dot3(T0[0], c[0], T0[1], c[1], T0[2], c[2]);
+    float A10 = dot3(T0[0], c[1], T0[1], c[3], T0[2], c[4]);
+    float A20 = dot3(T0[0], c[2], T0[1], c[4], T0[2], c[5]);
+    float A01 = dot3(T1[0], c[0], T1[1], c[1], T1[2], c[2]);
+    float A11 = dot3(T1[0], c[1], T1[1], c[3], T1[2], c[4]);
+    float A21 = dot3(T1[0], c[2], T1[1], c[4], T1[2], c[5]);
+    cov00 = fadd(dot3(A00, T0[0], A10, T0[1], A20, T0[2]), 0.3f);
+    cov01 = dot3(A01, T0[0], A11, T0[1], A21, T0[2]);
+    cov11 = fadd(dot3(A01, T1[0], A11, T1[1], A21, T1[2]), 0.3f);
+}
+
+constexpr float SH_C0 = 0.28209479177387814f;
+constexpr float SH_C1 = 0.4886025119029199f;
+constexpr float SH_C2_0 = 1.0925484305920792f, SH_C2_1 = -1.0925484305920792f, SH_C2_2 = 0.31539156525252005f,
+                SH_C2_3 = -1.0925484305920792f, SH_C2_4 = 0.5462742152960396f;
+constexpr float SH_C3_0 = -0.5900435899266435f, SH_C3_1 = 2.890611442640554f, SH_C3_2 = -0.4570457994644658f,
+                SH_C3_3 = 0.3731763325901154f, SH_C3_4 = -0.4570457994644658f, SH_C3_5 = 1.445305721320277f,
+                SH_C3_6 = -0.5900435899266435f;
+
+template <bool COMPAT>
+__global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(const PreprocessParams p, const int vec_means,
+                                                                 const int vec_scales, const int vec_sh) {
+    __shared__ __align__(16) float s_means[PRE_THREADS * 3];
+    __shared__ __align__(16) float s_scales[PRE_THREADS * 3];
+    __shared__ float s_cam[36];                       // view[16] proj[16] cam_pos[3]
+    __shared__ float4 s_queue[PRE_THREADS / 32][32];  // per-warp survivors: dir.xyz, idx
+    __shared__ uint32_t s_wsum[PRE_THREADS / 32];
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int base = blockIdx.x * PRE_THREADS;
+    const int idx = base + tid;
+    const int nvalid = min(PRE_THREADS, p.P - base);
+    const bool valid = tid < nvalid;
+
+    // ---- stage camera + float3 streams -------------------------------------------------
+    if (tid < 16) s_cam[tid] = __ldg(p.viewmatrix + tid);
+    else if (tid < 32) s_cam[tid] = __ldg(p.projmatrix + (tid - 16));
+    else if (tid < 35 && p.cam_pos) s_cam[tid] = __ldg(p.cam_pos + (tid - 32));
+
+    if (p.means_stride == 3) {
+        const float* g = p.means3D + (size_t)base * 3;
+        const int nf = nvalid * 3;
+        if (vec_means) {
+            const int nv = nf >> 2;
+            if (tid < nv) reinterpret_cast<float4*>(s_means)[tid] = ldg_f4(g + tid * 4);
+            for (int i = (nv << 2) + tid; i < nf; i += PRE_THREADS) s_means[i] = __ldg(g + i);
+        } else {
+            for (int i = tid; i < nf; i += PRE_THREADS) s_means[i] = __ldg(g + i);
+        }
+    }
+    const bool need_scales = (p.cov3D_precomp == nullptr);
+    if (need_scales && p.scales_stride == 3) {
+        const float* g = p.scales + (size_t)base * 3;
+        const int nf = nvalid * 3;
+        if (vec_scales) {
+            const int nv = nf >> 2;
+            if (tid < nv) reinterpret_cast<float4*>(s_scales)[tid] = ldg_f4(g + tid * 4);
+            for (int i = (nv << 2) + tid; i < nf; i += PRE_THREADS) s_scales[i] = __ldg(g + i);
+        } else {
+            for (int i = tid; i < nf; i += PRE_THREADS) s_scales[i] = __ldg(g + i);
+        }
+    }
+    __syncthreads();
+
+    const float* v = s_cam;
+    const float* pm = s_cam + 16;
+
+    uint32_t tiles = 0;
+    bool need_sh = false;
+    float dirx = 0.f, diry = 0.f, dirz = 0.f;
+
+    if (valid) {
+        int radius_out = 0;
+        float px, py, pz, pw = 1.0f;
+        if (p.means_stride == 3) {
+            px = s_means[3 * tid]; py = s_means[3 * tid + 1]; pz = s_means[3 * tid + 2];
+        } else {
+            float4 m = ldg_f4(p.means3D + (size_t)idx * 4);
+            px = m.x; py = m.y; pz = m.z; pw = m.w;
+        }
+
+        bool alive = true;
+        float tvx, tvy, tvz;  // view-space point used by the EWA projection
+        float prx, pry;       // NDC x, y
+        float depth;
+
+        if (!COMPAT) {
+            // in_frustum: view-space z only (upstream auxiliary.h); transformPoint4x3 left to right
+            tvx = fadd(dot3(v[0], px, v[4], py, v[8], pz), v[12]);
+            tvy = fadd(dot3(v[1], px, v[5], py, v[9], pz), v[13]);
+            tvz = fadd(dot3(v[2], px, v[6], py, v[10], pz), v[14]);
+            if (tvz <= 0.2f) alive = false;
+            float hx = fadd(dot3(pm[0], px, pm[4], py, pm[8], pz), pm[12]);
+            float hy = fadd(dot3(pm[1], px, pm[5], py, pm[9], pz), pm[13]);
+            float hw = fadd(dot3(pm[3], px, pm[7], py, pm[11], pz), pm[15]);
+            float p_w = frcp(fadd(hw, 0.0000001f));
+            prx = fmul(hx, p_w);
+            pry = fmul(hy, p_w);
+            depth = tvz;
+            // SIBR bounding-box cull
+            if (px < p.boxmin[0] || py < p.boxmin[1] || pz < p.boxmin[2] || px > p.boxmax[0] || py > p.boxmax[1] ||
+                pz > p.boxmax[2])
+                alive = false;
+        } else {
+            // GSCuda.cu:302-309: glm mat4*vec4 = (m0*x + m1*y) + (m2*z + m3*w)
+            float hx = fadd(fadd(fmul(pm[0], px), fmul(pm[4], py)), fadd(fmul(pm[8], pz), fmul(pm[12], pw)));
+            float hy = fadd(fadd(fmul(pm[1], px), fmul(pm[5], py)), fadd(fmul(pm[9], pz), fmul(pm[13], pw)));
+            float hz = fadd(fadd(fmul(pm[2], px), fmul(pm[6], py)), fadd(fmul(pm[10], pz), fmul(pm[14], pw)));
+            float hw = fadd(fadd(fmul(pm[3], px), fmul(pm[7], py)), fadd(fmul(pm[11], pz), fmul(pm[15], pw)));
+            float oow = frcp(fadd(0.001f, hw));
+            prx = fmul(oow, hx);
+            pry = fmul(oow, hy);
+            float prz = fmul(oow, hz);
+            if (prz < 0.0f || prz > 1.0f || prx < -1.3f || prx > 1.3f || pry < -1.3f || pry > 1.3f) alive = false;
+            depth = prz;
+            // computeCov2D's own transform: view * vec4(mean, 1.0f)   (GSCuda.cu:202)
+            tvx = fadd(fadd(fmul(v[0], px), fmul(v[4], py)), fadd(fmul(v[8], pz), fmul(v[12], 1.0f)));
+            tvy = fadd(fadd(fmul(v[1], px), fmul(v[5], py)), fadd(fmul(v[9], pz), fmul(v[13], 1.0f)));
+            tvz = fadd(fadd(fmul(v[2], px), fmul(v[6], py)), fadd(fmul(v[10], pz), fmul(v[14], 1.0f)));
+        }
+
+        float cov00 = 0.f, cov01 = 0.f, cov11 = 0.f;
+        if (alive) {
+            // ---- 3D covariance ---------------------------------------------------------
+            float c[6];
+            if (p.cov3D_precomp) {
+                const float* cp = p.cov3D_precomp + (size_t)idx * 6;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) c[i] = __ldg(cp + i);
+            } else {
+                float sx, sy, sz;
+                if (p.scales_stride == 3) {
+                    sx = s_scales[3 * tid]; sy = s_scales[3 * tid + 1]; sz = s_scales[3 * tid + 2];
+                } else {
+                    float4 s4 = ldg_f4(p.scales + (size_t)idx * 4);
+                    sx = s4.x; sy = s4.y; sz = s4.z;
+                }
+                const float4 q = ldg_f4(p.rotations + (size_t)idx * 4);
+                const float s0 = fmul(p.scale_modifier, sx), s1 = fmul(p.scale_modifier, sy),
+                            s2 = fmul(p.scale_modifier, sz);
+                if (!COMPAT) {
+                    const float r = q.x, x = q.y, y = q.z, z = q.w;
+                    // R.c[col][row] exactly as the glm::mat3 constructor receives it
+                    float R00 = fsub(1.f, fmul(2.f, fadd(fmul(y, y), fmul(z, z))));
+                    float R01 = fmul(2.f, fsub(fmul(x, y), fmul(r, z)));
+                    float R02 = fmul(2.f, fadd(fmul(x, z), fmul(r, y)));
+                    float R10 = fmul(2.f, fadd(fmul(x, y), fmul(r, z)));
+                    float R11 = fsub(1.f, fmul(2.f, fadd(fmul(x, x), fmul(z, z))));
+                    float R12 = fmul(2.f, fsub(fmul(y, z), fmul(r, x)));
+                    float R20 = fmul(2.f, fsub(fmul(x, z), fmul(r, y)));
+                    float R21 = fmul(2.f, fadd(fmul(y, z), fmul(r, x)));
+                    float R22 = fsub(1.f, fmul(2.f, fadd(fmul(x, x), fmul(y, y))));
+                    // M = S * R  ->  M.c[c][k] = s_k * R.c[c][k]
+                    float M00 = fmul(s0, R00), M01 = fmul(s1, R01), M02 = fmul(s2, R02);
+                    float M10 = fmul(s0, R10), M11 = fmul(s1, R11), M12 = fmul(s2, R12);
+                    float M20 = fmul(s0, R20), M21 = fmul(s1, R21), M22 = fmul(s2, R22);
+                    // Sigma = M^T * M  ->  Sigma.c[c][r] = sum_k M.c[r][k] * M.c[c][k]
+                    c[0] = dot3(M00, M00, M01, M01, M02, M02);
+                    c[1] = dot3(M10, M00, M11, M01, M12, M02);
+                    c[2] = dot3(M20, M00, M21, M01, M22, M02);
+                    c[3] = dot3(M10, M10, M11, M11, M12, M12);
+                    c[4] = dot3(M20, M10, M21, M11, M22, M12);
+                    c[5] = dot3(M20, M20, M21, M21, M22, M22);
+                } else {
+                    // glm::normalize(vec4): v * (1/sqrt(dot)), dot pairwise   (GSCuda.cu:178)
+                    float d = fadd(fadd(fmul(q.x, q.x), fmul(q.y, q.y)), fadd(fmul(q.z, q.z), fmul(q.w, q.w)));
+                    float inv = frcp(fsqrt(d));
+                    float qx = fmul(q.x, inv), qy = fmul(q.y, inv), qz = fmul(q.z, inv), qw = fmul(q.w, inv);
+                    // quatToMat (GSCuda.cu:157-162): float inner sums, double outer 2.0* / -1.0
+#define GSR_D1(sum) __double2float_rn(__dadd_rn(__dmul_rn(2.0, (double)(sum)), -1.0))
+#define GSR_D2(val) __double2float_rn(__dmul_rn(2.0, (double)(val)))
+                    float R00 = GSR_D1(fadd(fmul(qx, qx), fmul(qy, qy)));
+                    float R01 = GSR_D2(fadd(fmul(qy, qz), fmul(qx, qw)));
+                    float R02 = GSR_D2(fsub(fmul(qy, qw), fmul(qx, qz)));
+                    float R10 = GSR_D2(fsub(fmul(qy, qz), fmul(qx, qw)));
+                    float R11 = GSR_D1(fadd(fmul(qx, qx), fmul(qz, qz)));
+                    float R12 = GSR_D2(fadd(fmul(qz, qw), fmul(qx, qy)));
+                    float R20 = GSR_D2(fadd(fmul(qy, qw), fmul(qx, qz)));
+                    float R21 = GSR_D2(fsub(fmul(qz, qw), fmul(qx, qy)));
+                    float R22 = GSR_D1(fadd(fmul(qx, qx), fmul(qw, qw)));
+#undef GSR_D1
+#undef GSR_D2
+                    // rs = R * S -> rs.c[c][r] = R.c[c][r] * s_c ; sigma = rs * rs^T ->
+                    // sigma.c[c][r] = sum_k rs.c[k][r] * rs.c[k][c]
+                    float a00 = fmul(R00, s0), a01 = fmul(R01, s0), a02 = fmul(R02, s0);
+                    float a10 = fmul(R10, s1), a11 = fmul(R11, s1), a12 = fmul(R12, s1);
+                    float a20 = fmul(R20, s2), a21 = fmul(R21, s2), a22 = fmul(R22, s2);
+                    c[0] = dot3(a00, a00, a10, a10, a20, a20);  // sigma[0][0]
+                    c[1] = dot3(a00, a01, a10, a11, a20, a21);  // sigma[1][0]: c=1, r=0
+                    c[2] = dot3(a00, a02, a10, a12, a20, a22);  // sigma[2][0]
+                    c[3] = dot3(a01, a01, a11, a11, a21, a21);  // sigma[1][1]
+                    c[4] = dot3(a01, a02, a11, a12, a21, a22);  // sigma[2][1]: c=2, r=1
+                    c[5] = dot3(a02, a02, a12, a12, a22, a22);  // sigma[2][2]
+                }
+                float* co = p.cov3D + (size_t)idx * 6;
+                reinterpret_cast<float2*>(co)[0] = make_float2(c[0], c[1]);
+                reinterpret_cast<float2*>(co)[1] = make_float2(c[2], c[3]);
+                reinterpret_cast<float2*>(co)[2] = make_float2(c[4], c[5]);
+            }
+
+            // ---- EWA projection (computeCov2D) -----------------------------------------
+            const float limx = fmul(1.3f, p.tan_fovx), limy = fmul(1.3f, p.tan_fovy);
+            const float txtz = fdiv(tvx, tvz), tytz = fdiv(tvy, tvz);
+            float tx, ty;
+            if (!COMPAT) {
+                tx = fmul(fminf(limx, fmaxf(-limx, txtz)), tvz);
+                ty = fmul(fminf(limy, fmaxf(-limy, tytz)), tvz);
+            } else {
+                tx = fmul(glm_min(limx, glm_max(-limx, txtz)), tvz);
+                ty = fmul(glm_min(limy, glm_max(-limy, tytz)), tvz);
+            }
+            const float fx = COMPAT ? p.focal_y : p.focal_x;  // in-tree: single focalDist (GSCuda.cu:721)
+            const float fy = p.focal_y;
+            const float tz2 = fmul(tvz, tvz);
+            const float j00 = fdiv(fx, tvz), j02 = fdiv(-fmul(fx, tx), tz2);
+            const float j11 = fdiv(fy, tvz), j12 = fdiv(-fmul(fy, ty), tz2);
+            float T0[3], T1[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                T0[r] = fadd(fmul(v[4 * r], j00), fmul(v[4 * r + 2], j02));
+                T1[r] = fadd(fmul(v[4 * r + 1], j11), fmul(v[4 * r + 2], j12));
+            }
+            project_cov(T0, T1, c, cov00, cov01, cov11);
+        }
+
+        float det = fsub(fmul(cov00, cov11), fmul(cov01, cov01));
+        if (alive && det == 0.0f) alive = false;
+
+        if (alive) {
+            const float det_inv = frcp(det);
+            const float conx = fmul(cov11, det_inv), cony = fmul(-cov01, det_inv), conz = fmul(cov00, det_inv);
+            const float mid = fmul(0.5f, fadd(cov00, cov11));
+            float disc;
+            if (!COMPAT) disc = fsqrt(fmaxf(0.1f, fsub(fmul(mid, mid), det)));
+            else disc = fsqrt(glm_max(0.1f, fsub(fmul(mid, mid), det)));
+            const float l1 = fadd(mid, disc), l2 = fsub(mid, disc);
+            const float my_radius = ceilf(fmul(3.f, fsqrt(COMPAT ? glm_max(l1, l2) : fmaxf(l1, l2))));
+            float ix, iy;
+            if (!COMPAT) {
+                ix = ndc2pix(prx, p.W);
+                iy = ndc2pix(pry, p.H);
+            } else {
+                ix = fmul(fadd(fmul(prx, 0.5f), 0.5f), (float)p.W);  // GSCuda.cu:342
+                iy = fmul(fadd(fmul(pry, 0.5f), 0.5f), (float)p.H);
+            }
+            int minx, miny, maxx, maxy;
+            const int ri = __float2int_rz(my_radius);
+            if (p.rects == nullptr) {
+                get_rect(ix, iy, ri, ri, p.grid_x, p.grid_y, minx, miny, maxx, maxy);
+            } else {
+                const int rx = __float2int_rz(ceilf(fmul(3.f, fsqrt(cov00))));
+                const int ry = COMPAT ? __float2int_rz(ceilf(fmul(3.0f, cov11)))  // GSCuda.cu:352 (no sqrt)
+                                      : __float2int_rz(ceilf(fmul(3.f, fsqrt(cov11))));
+                reinterpret_cast<int2*>(p.rects)[idx] = make_int2(rx, ry);
+                get_rect(ix, iy, rx, ry, p.grid_x, p.grid_y, minx, miny, maxx, maxy);
+            }
+            const uint32_t area = (uint32_t)(maxx - minx) * (uint32_t)(maxy - miny);
+            if (area != 0) {
+                tiles = area;
+                radius_out = ri;
+                p.depths[idx] = depth;
+                reinterpret_cast<float2*>(p.means2D)[idx] = make_float2(ix, iy);
+                reinterpret_cast<float4*>(p.conic_opacity)[idx] = make_float4(conx, cony, conz, __ldg(p.opacities + idx));
+                if (p.colors_precomp == nullptr) {
+                    if (!COMPAT) {
+                        need_sh = true;
+                        float dx = fsub(px, s_cam[32]), dy = fsub(py, s_cam[33]), dz = fsub(pz, s_cam[34]);
+                        float len = fsqrt(fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz)));
+                        dirx = fdiv(dx, len); diry = fdiv(dy, len); dirz = fdiv(dz, len);
+                    } else {
+                        const float* sh = p.shs + (size_t)idx * 48;  // GSCuda.cu:364-365
+                        float* o = p.rgb + (size_t)idx * 3;
+                        o[0] = fadd(0.5f, fmul(0.4f, __ldg(sh + 0)));
+                        o[1] = fadd(0.5f, fmul(0.4f, __ldg(sh + 1)));
+                        o[2] = fadd(0.5f, fmul(0.4f, __ldg(sh + 2)));
+                    }
+                }
+            }
+        }
+        p.radii[idx] = radius_out;
+        p.tiles_touched[idx] = tiles;
+    }
+
+    // ---- SH colour: 4 lanes per surviving Gaussian -----------------------------------------
+    if (!COMPAT) {
+        const unsigned mask = __ballot_sync(0xffffffffu, need_sh);
+        if (mask) {
+            if (need_sh) {
+                const int pos = __popc(mask & ((1u << lane) - 1u));
+                s_queue[warp][pos] = make_float4(dirx, diry, dirz, __int_as_float(idx));
+            }
+            __syncwarp();
+            const int n = __popc(mask);
+            const int q = lane & 3;
+            const int ncoef = min(p.M, (p.D + 1) * (p.D + 1));
+            const int nk = max(0, min(4, ncoef - 4 * q));  // coefficients this lane owns: 4q .. 4q+nk-1
+            for (int r0 = 0; r0 < n; r0 += 8) {
+                const int slot = r0 + (lane >> 2);
+                const bool act = slot < n;
+                float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+                int gidx = 0;
+                float t[4][3];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) t[k][0] = t[k][1] = t[k][2] = 0.f;
+                if (act) {
+                    const float4 e = s_queue[warp][slot];
+                    gidx = __float_as_int(e.w);
+                    const float x = e.x, y = e.y, z = e.z;
+                    float s[12];
+                    const float* sp = p.shs + ((size_t)gidx * p.M + 4 * q) * 3;
+                    if (nk == 4 && vec_sh) {
+                        float4 a = ldg_f4(sp), b = ldg_f4(sp + 4), cc = ldg_f4(sp + 8);
+                        s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w;
+                        s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+                        s[8] = cc.x; s[9] = cc.y; s[10] = cc.z; s[11] = cc.w;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 12; ++i) s[i] = (i < nk * 3) ? __ldg(sp + i) : 0.f;
+                    }
+                    const float xx = fmul(x, x), yy = fmul(y, y), zz = fmul(z, z);
+                    const float xy = fmul(x, y), yz = fmul(y, z), xz = fmul(x, z);
+                    float b0, b1, b2, b3;  // basis factor of each owned coefficient (sign folded in)
+                    if (q == 0) {
+                        b0 = SH_C0;
+                        b1 = -fmul(SH_C1, y);
+                        b2 = fmul(SH_C1, z);
+                        b3 = -fmul(SH_C1, x);
+                    } else if (q == 1) {
+                        b0 = fmul(SH_C2_0, xy);
+                        b1 = fmul(SH_C2_1, yz);
+                        b2 = fmul(SH_C2_2, fsub(fsub(fmul(2.0f, zz), xx), yy));
+                        b3 = fmul(SH_C2_3, xz);
+                    } else if (q == 2) {
+                        b0 = fmul(SH_C2_4, fsub(xx, yy));
+                        b1 = fmul(fmul(SH_C3_0, y), fsub(fmul(3.0f, xx), yy));
+                        b2 = fmul(fmul(SH_C3_1, xy), z);
+                        b3 = fmul(fmul(SH_C3_2, y), fsub(fsub(fmul(4.0f, zz), xx), yy));
+                    } else {
+                        b0 = fmul(fmul(SH_C3_3, z), fsub(fsub(fmul(2.0f, zz), fmul(3.0f, xx)), fmul(3.0f, yy)));
+                        b1 = fmul(fmul(SH_C3_4, x), fsub(fsub(fmul(4.0f, zz), xx), yy));
+                        b2 = fmul(fmul(SH_C3_5, z), fsub(xx, yy));
+                        b3 = fmul(fmul(SH_C3_6, x), fsub(xx, fmul(3.0f, yy)));
+                    }
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        t[0][ch] = fmul(b0, s[ch]);
+                        t[1][ch] = fmul(b1, s[3 + ch]);
+                        t[2][ch] = fmul(b2, s[6 + ch]);
+                        t[3][ch] = fmul(b3, s[9 + ch]);
+                    }
+                }
+                // Chain the partial sums lane 0 -> 1 -> 2 -> 3 so the additions happen in the
+                // reference's coefficient order (bit-identical colours and clamp flags).
+#pragma unroll
+                for (int step = 0; step < 4; ++step) {
+                    const float p0 = __shfl_up_sync(0xffffffffu, acc0, 1);
+                    const float p1 = __shfl_up_sync(0xffffffffu, acc1, 1);
+                    const float p2 = __shfl_up_sync(0xffffffffu, acc2, 1);
+                    if (q == step) {
+                        if (step == 0) {
+                            acc0 = t[0][0]; acc1 = t[0][1]; acc2 = t[0][2];
+                        } else {
+                            acc0 = p0; acc1 = p1; acc2 = p2;
+                            if (nk > 0) { acc0 = fadd(acc0, t[0][0]); acc1 = fadd(acc1, t[0][1]); acc2 = fadd(acc2, t[0][2]); }
+                        }
+                        if (nk > 1) { acc0 = fadd(acc0, t[1][0]); acc1 = fadd(acc1, t[1][1]); acc2 = fadd(acc2, t[1][2]); }
+                        if (nk > 2) { acc0 = fadd(acc0, t[2][0]); acc1 = fadd(acc1, t[2][1]); acc2 = fadd(acc2, t[2][2]); }
+                        if (nk > 3) { acc0 = fadd(acc0, t[3][0]); acc1 = fadd(acc1, t[3][1]); acc2 = fadd(acc2, t[3][2]); }
+                    }
+                }
+                if (act && q == 3) {
+                    acc0 = fadd(acc0, 0.5f); acc1 = fadd(acc1, 0.5f); acc2 = fadd(acc2, 0.5f);
+                    unsigned char* cl = p.clamped + (size_t)gidx * 3;
+                    cl[0] = acc0 < 0.f; cl[1] = acc1 < 0.f; cl[2] = acc2 < 0.f;
+                    float* o = p.rgb + (size_t)gidx * 3;
+                    o[0] = fmaxf(acc0, 0.f); o[1] = fmaxf(acc1, 0.f); o[2] = fmaxf(acc2, 0.f);
+                }
+            }
+        }
+    }
+
+    // ---- per-block partial sum for the tiles_touched scan --------------------------------
+    const uint32_t wsum = __reduce_add_sync(0xffffffffu, tiles);
+    if (lane == 0) s_wsum[warp] = wsum;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int w = 0; w < PRE_THREADS / 32; ++w) t += s_wsum[w];
+        p.block_sums[blockIdx.x] = t;
+    }
+}
+
+}  // namespace
+
+int launch_preprocess(const PreprocessParams& p, bool compat, cudaStream_t s) {
+    if (p.P <= 0) return 0;
+    const int blocks = (p.P + PRE_THREADS - 1) / PRE_THREADS;
+    const int vec_means = (p.means_stride == 3) && ((reinterpret_cast<uintptr_t>(p.means3D) & 15) == 0);
+    const int vec_scales = p.scales && (p.scales_stride == 3) && ((reinterpret_cast<uintptr_t>(p.scales) & 15) == 0);
+    const int vec_sh = p.shs && ((reinterpret_cast<uintptr_t>(p.shs) & 15) == 0) && ((p.M * 3) % 4 == 0);
+    if (compat)
+        preprocess_kernel<true><<<blocks, PRE_THREADS, 0, s>>>(p, vec_means, vec_scales, vec_sh);
+    else
+        preprocess_kernel<false><<<blocks, PRE_THREADS, 0, s>>>(p, vec_means, vec_scales, vec_sh);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return -(int)e;
+    return 1;
+}
+
+}  // namespace gsr

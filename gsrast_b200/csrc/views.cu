@@ -1,0 +1,259 @@
+// views.cu — resident-scene renderer for streams / batches of camera views, and the one-shot
+// repack of GSRast's viewer buffers into the contract layout.
+//
+// gsr_renderer mirrors the host object that owns the splat draw path in the reference,
+// GSGaussians (/root/reference/apps/gsrast/GSGaussians.{hpp,cpp}):
+//   constructor + configureFromSplatData (GSGaussians.cpp:44-153)  -> gsr_renderer_create
+//   resizeFunctional grow-only scratch (GSGaussians.cpp:27-42)     -> Lane::{geom,binning,img}
+//   draw(): upload view/proj/camPos, call forward (:155-212)       -> gsr_renderer_render*
+// What is B200-first: two lanes (stream + scratch + pinned readback slot each) alternate
+// views, so the 4-byte num_rendered round trip of view k+1 hides behind the sort/blend of
+// view k, camera matrices travel as one 144-byte pinned async copy instead of three blocking
+// cudaMemcpy + cudaDeviceSynchronize (CudaBuffer.hpp:42-49), and frames can stream back to
+// pinned host memory while the next view renders.  A single frame is never split.
+#include <cstring>
+#include <new>
+
+#include "gsr_common.cuh"
+
+namespace gsr {
+
+namespace {
+
+constexpr int LANES = 2;
+constexpr int CAM_FLOATS = 36;  // view[16] proj[16] cam_pos[3] pad[1]
+
+struct Chunk {
+    void* ptr = nullptr;
+    size_t size = 0;
+};
+
+// resizeFunctional (GSGaussians.cpp:27-42): grow-only, over-allocates 2x, same base otherwise.
+char* chunk_alloc(size_t n, void* user) {
+    Chunk* c = static_cast<Chunk*>(user);
+    if (n > c->size) {
+        if (c->ptr) cudaFree(c->ptr);
+        c->ptr = nullptr;
+        c->size = 0;
+        if (cudaMalloc(&c->ptr, 2 * n) != cudaSuccess) return nullptr;
+        c->size = 2 * n;
+    }
+    return static_cast<char*>(c->ptr);
+}
+
+struct Lane {
+    cudaStream_t stream = nullptr;
+    Chunk geom, binning, img;
+    HostSlot slot;
+    float* cam_dev = nullptr;   // [CAM_FLOATS]
+    float* cam_host = nullptr;  // pinned
+    float* frame_dev = nullptr; // [3*H*W], only for host-output rendering
+    cudaEvent_t cam_free = nullptr;  // cam_host may be overwritten once this fired
+    cudaEvent_t done = nullptr;
+    bool cam_pending = false;
+};
+
+}  // namespace
+
+struct Renderer {
+    int P, D, M, W, H;
+    const float *means3D, *shs, *colors_precomp, *opacities, *scales, *rotations, *background;
+    float scale_modifier;
+    unsigned flags;
+    cudaStream_t user_stream;
+    Lane lane[LANES];
+    cudaEvent_t ready = nullptr;
+    gsr_stage_times last;
+    bool want_times = false;
+};
+
+namespace {
+
+int lane_init(Lane& l) {
+    GSR_CUDA_TRY(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+    GSR_CUDA_TRY(cudaMalloc(&l.cam_dev, CAM_FLOATS * sizeof(float)));
+    GSR_CUDA_TRY(cudaHostAlloc(&l.cam_host, CAM_FLOATS * sizeof(float), cudaHostAllocDefault));
+    GSR_CUDA_TRY(cudaEventCreateWithFlags(&l.cam_free, cudaEventDisableTiming));
+    GSR_CUDA_TRY(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+    return ensure_slot(l.slot);
+}
+
+void lane_destroy(Lane& l) {
+    if (l.stream) cudaStreamSynchronize(l.stream);
+    if (l.geom.ptr) cudaFree(l.geom.ptr);
+    if (l.binning.ptr) cudaFree(l.binning.ptr);
+    if (l.img.ptr) cudaFree(l.img.ptr);
+    if (l.cam_dev) cudaFree(l.cam_dev);
+    if (l.cam_host) cudaFreeHost(l.cam_host);
+    if (l.frame_dev) cudaFree(l.frame_dev);
+    if (l.cam_free) cudaEventDestroy(l.cam_free);
+    if (l.done) cudaEventDestroy(l.done);
+    release_slot(l.slot);
+    if (l.stream) cudaStreamDestroy(l.stream);
+}
+
+// One view on one lane: camera H2D + forward, all on the lane's stream.
+int render_one(Renderer* r, Lane& l, const float* cam36, float tan_fovx, float tan_fovy, float* out_dev,
+               gsr_stage_times* times) {
+    if (l.cam_pending) {  // previous upload from cam_host must have been consumed
+        GSR_CUDA_TRY(cudaEventSynchronize(l.cam_free));
+        l.cam_pending = false;
+    }
+    memcpy(l.cam_host, cam36, CAM_FLOATS * sizeof(float));
+    GSR_CUDA_TRY(cudaMemcpyAsync(l.cam_dev, l.cam_host, CAM_FLOATS * sizeof(float), cudaMemcpyHostToDevice, l.stream));
+    GSR_CUDA_TRY(cudaEventRecord(l.cam_free, l.stream));
+    l.cam_pending = true;
+
+    gsr_forward_args a;
+    memset(&a, 0, sizeof(a));
+    a.geometry_alloc = chunk_alloc; a.geometry_user = &l.geom;
+    a.binning_alloc = chunk_alloc;  a.binning_user = &l.binning;
+    a.image_alloc = chunk_alloc;    a.image_user = &l.img;
+    a.P = r->P; a.D = r->D; a.M = r->M; a.background = r->background; a.width = r->W; a.height = r->H;
+    const bool compat = (r->flags & GSR_FLAG_GSRAST_COMPAT) != 0;
+    a.means3D = r->means3D; a.means_stride = compat ? 4 : 3;
+    a.shs = r->shs; a.colors_precomp = r->colors_precomp; a.opacities = r->opacities;
+    a.scales = r->scales; a.scales_stride = compat ? 4 : 3;
+    a.scale_modifier = r->scale_modifier; a.rotations = r->rotations;
+    a.viewmatrix = l.cam_dev; a.projmatrix = l.cam_dev + 16; a.cam_pos = l.cam_dev + 32;
+    a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy;
+    a.out_color = out_dev;
+    a.stream = l.stream;
+    a.flags = r->flags;
+    a.timings = times;
+    return forward_impl(&a, &l.slot);
+}
+
+// vec4 means/scales -> float3; PLY-order SH (f_dc[3], f_rest[c*15+k-1]) -> [16][3] interleaved.
+// (apps/gsrast/SplatData.hpp:17-25, SplatData.cpp:48-58, GSGaussians.cpp:121-134)
+__global__ void repack_kernel(int P, const float4* __restrict__ means4, const float4* __restrict__ scales4,
+                              const float* __restrict__ shs_raw, float* __restrict__ means3,
+                              float* __restrict__ scales3, float* __restrict__ shs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    if (means4 && means3) {
+        const float4 m = means4[i];
+        means3[3 * i] = m.x; means3[3 * i + 1] = m.y; means3[3 * i + 2] = m.z;
+    }
+    if (scales4 && scales3) {
+        const float4 s = scales4[i];
+        scales3[3 * i] = s.x; scales3[3 * i + 1] = s.y; scales3[3 * i + 2] = s.z;
+    }
+    if (shs_raw && shs) {
+        const float* in = shs_raw + (size_t)i * 48;
+        float* out = shs + (size_t)i * 48;
+        out[0] = in[0]; out[1] = in[1]; out[2] = in[2];
+        for (int k = 1; k < 16; ++k)
+            for (int c = 0; c < 3; ++c) out[k * 3 + c] = in[3 + c * 15 + (k - 1)];
+    }
+}
+
+}  // namespace
+
+}  // namespace gsr
+
+using namespace gsr;
+
+extern "C" {
+
+void gsr_renderer_destroy(void* h) {
+    Renderer* r = static_cast<Renderer*>(h);
+    if (!r) return;
+    for (auto& l : r->lane) lane_destroy(l);
+    if (r->ready) cudaEventDestroy(r->ready);
+    delete r;
+}
+
+void* gsr_renderer_create(int P, int D, int M, const float* means3D, const float* shs, const float* colors_precomp,
+                          const float* opacities, const float* scales, const float* rotations,
+                          const float* background, float scale_modifier, int width, int height, void* stream,
+                          unsigned flags) {
+    if (P < 0 || width <= 0 || height <= 0 || !background) return nullptr;
+    Renderer* r = new (std::nothrow) Renderer();
+    if (!r) return nullptr;
+    r->P = P; r->D = D; r->M = M; r->W = width; r->H = height;
+    r->means3D = means3D; r->shs = shs; r->colors_precomp = colors_precomp; r->opacities = opacities;
+    r->scales = scales; r->rotations = rotations; r->background = background;
+    r->scale_modifier = scale_modifier; r->flags = flags;
+    r->user_stream = static_cast<cudaStream_t>(stream);
+    memset(&r->last, 0, sizeof(r->last));
+    bool ok = cudaEventCreateWithFlags(&r->ready, cudaEventDisableTiming) == cudaSuccess;
+    for (auto& l : r->lane) ok = ok && lane_init(l) == 0;
+    if (!ok) {
+        gsr_renderer_destroy(r);
+        return nullptr;
+    }
+    return r;
+}
+
+// cameras: HOST float[n_views][36] (view[16], proj[16], cam_pos[3], pad); out_color: DEVICE
+// float[n_views][3][H][W]; num_rendered: HOST int[n_views] or NULL.  Work is ordered after
+// everything already queued on the renderer's stream and that stream waits for the frames.
+int gsr_renderer_render(void* h, const float* cameras, int n_views, float tan_fovx, float tan_fovy, float* out_color,
+                        int* num_rendered, void* timings) {
+    Renderer* r = static_cast<Renderer*>(h);
+    if (!r || !cameras || !out_color || n_views < 0) return GSR_ERR_INVALID_ARG;
+    GSR_CUDA_TRY(cudaEventRecord(r->ready, r->user_stream));
+    for (auto& l : r->lane) GSR_CUDA_TRY(cudaStreamWaitEvent(l.stream, r->ready, 0));
+    const size_t frame = (size_t)3 * r->W * r->H;
+    long long total = 0;
+    for (int v = 0; v < n_views; ++v) {
+        // stage timings need the whole pipeline on one lane, otherwise alternate
+        Lane& l = r->lane[timings ? 0 : (v % LANES)];
+        int rc = render_one(r, l, cameras + (size_t)v * CAM_FLOATS, tan_fovx, tan_fovy, out_color + (size_t)v * frame,
+                            timings ? &r->last : nullptr);
+        if (rc < 0) return rc;
+        if (num_rendered) num_rendered[v] = rc;
+        total += rc;
+    }
+    for (auto& l : r->lane) {
+        GSR_CUDA_TRY(cudaEventRecord(l.done, l.stream));
+        GSR_CUDA_TRY(cudaStreamWaitEvent(r->user_stream, l.done, 0));
+    }
+    if (timings) memcpy(timings, &r->last, sizeof(r->last));
+    return (int)(total > 0x7fffffffLL ? 0x7fffffff : total);
+}
+
+// Same, but every frame is copied to HOST memory out_color[n_views][3][H][W] (pinned memory
+// makes the copy asynchronous) while the next view renders; returns after all frames landed.
+int gsr_renderer_render_host(void* h, const float* cameras, int n_views, float tan_fovx, float tan_fovy,
+                             float* out_color_host, int* num_rendered) {
+    Renderer* r = static_cast<Renderer*>(h);
+    if (!r || !cameras || !out_color_host || n_views < 0) return GSR_ERR_INVALID_ARG;
+    const size_t frame = (size_t)3 * r->W * r->H;
+    for (auto& l : r->lane)
+        if (!l.frame_dev) GSR_CUDA_TRY(cudaMalloc(&l.frame_dev, frame * sizeof(float)));
+    GSR_CUDA_TRY(cudaEventRecord(r->ready, r->user_stream));
+    for (auto& l : r->lane) GSR_CUDA_TRY(cudaStreamWaitEvent(l.stream, r->ready, 0));
+    long long total = 0;
+    for (int v = 0; v < n_views; ++v) {
+        Lane& l = r->lane[v % LANES];
+        int rc = render_one(r, l, cameras + (size_t)v * CAM_FLOATS, tan_fovx, tan_fovy, l.frame_dev, nullptr);
+        if (rc < 0) return rc;
+        GSR_CUDA_TRY(cudaMemcpyAsync(out_color_host + (size_t)v * frame, l.frame_dev, frame * sizeof(float),
+                                     cudaMemcpyDeviceToHost, l.stream));
+        if (num_rendered) num_rendered[v] = rc;
+        total += rc;
+    }
+    for (auto& l : r->lane) GSR_CUDA_TRY(cudaStreamSynchronize(l.stream));
+    return (int)(total > 0x7fffffffLL ? 0x7fffffff : total);
+}
+
+int gsr_renderer_last_times(void* h, gsr_stage_times* out) {
+    Renderer* r = static_cast<Renderer*>(h);
+    if (!r || !out) return GSR_ERR_INVALID_ARG;
+    *out = r->last;
+    return 0;
+}
+
+int gsr_repack_gsrast_scene(int P, const float* means4, const float* scales4, const float* shs_raw, float* means3,
+                            float* scales3, float* shs, void* stream) {
+    if (P <= 0) return 0;
+    repack_kernel<<<(P + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        P, reinterpret_cast<const float4*>(means4), reinterpret_cast<const float4*>(scales4), shs_raw, means3, scales3,
+        shs);
+    cudaError_t e = cudaPeekAtLastError();
+    return e == cudaSuccess ? 1 : -(int)e;
+}
+
+}  // extern "C"

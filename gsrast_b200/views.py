@@ -1,0 +1,129 @@
+"""View-batch rendering on a resident scene and its sharding across GPUs.
+
+`ViewRenderer` wraps the native gsr_renderer (gsrast_b200/csrc/views.cu), the C form of the
+reference's GSGaussians object (apps/gsrast/GSGaussians.{hpp,cpp}: configureFromSplatData +
+draw()).  Multi-GPU: a batch of camera views is split across ranks, every rank
+holds the full Gaussian set, no collective sits on the data path; an optional gather brings
+the finished frames to rank 0 (NCCL over NVLink on GPUs, gloo in the CPU tests).  A single
+frame is never split.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def pack_cameras(cameras) -> np.ndarray:
+    """list[Camera] -> float32 [n,36] (view[16] proj[16] cam_pos[3] pad): the per-frame upload of
+    GSGaussians::draw (GSGaussians.cpp:171-173)."""
+    if isinstance(cameras, np.ndarray):
+        return np.ascontiguousarray(cameras, dtype=np.float32).reshape(-1, 36)
+    return np.ascontiguousarray(np.stack([c.packed() for c in cameras]).astype(np.float32))
+
+
+def shard_views(n_views: int, rank: int, world_size: int) -> list[int]:
+    """Round-robin assignment view v -> rank v % world_size (balanced to within one view)."""
+    return list(range(rank, n_views, world_size))
+
+
+def views_per_rank(n_views: int, world_size: int) -> int:
+    return (n_views + world_size - 1) // world_size
+
+
+class ViewRenderer:
+    def __init__(self, *, P, D, M, means3D, shs, colors_precomp, opacities, scales, rotations, background, width,
+                 height, scale_modifier=1.0, compat=False, flags=0, stream=None):
+        self._keep = (means3D, shs, colors_precomp, opacities, scales, rotations, background)
+        self.width, self.height = int(width), int(height)
+        self.device = means3D.device
+        p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        self._stream = stream
+        sp = (stream.cuda_stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream)
+        fl = int(flags) | (_lib.FLAG_GSRAST_COMPAT if compat else 0)
+        self._h = _lib.lib().gsr_renderer_create(int(P), int(D), int(M), p(means3D), p(shs), p(colors_precomp),
+                                                 p(opacities), p(scales), p(rotations), p(background),
+                                                 float(scale_modifier), self.width, self.height, sp, fl)
+        if not self._h:
+            raise RuntimeError("gsr_renderer_create failed")
+
+    @classmethod
+    def from_scene(cls, scene, width, height, device="cuda", background=(0.0, 0.0, 0.0), **kw):
+        dev = torch.device(device)
+        t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+        return cls(P=scene.P, D=scene.sh_degree, M=max(scene.max_coeffs, 1), means3D=t(scene.means3D), shs=t(scene.shs),
+                   colors_precomp=t(scene.colors_precomp), opacities=t(scene.opacities), scales=t(scene.scales),
+                   rotations=t(scene.rotations), background=torch.tensor(background, dtype=torch.float32, device=dev),
+                   width=width, height=height, **kw)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().gsr_renderer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def render(self, cameras, tan_fovx, tan_fovy, out=None, timings=False):
+        """Render n views into a device tensor [n,3,H,W].  Returns (out, num_rendered[n][, times])."""
+        cams = pack_cameras(cameras)
+        n = cams.shape[0]
+        if out is None:
+            out = torch.empty((n, 3, self.height, self.width), dtype=torch.float32, device=self.device)
+        nr = (C.c_int * max(n, 1))()
+        times = _lib.StageTimes() if timings else None
+        rc = _lib.lib().gsr_renderer_render(self._h, cams.ctypes.data, n, float(tan_fovx), float(tan_fovy),
+                                            out.data_ptr(), C.cast(nr, C.c_void_p),
+                                            C.cast(C.pointer(times), C.c_void_p) if timings else None)
+        _lib.check(rc)
+        res = (out, [int(nr[i]) for i in range(n)])
+        return res + (times.as_dict(),) if timings else res
+
+    def render_host(self, cameras, tan_fovx, tan_fovy, out_host=None):
+        """Render n views and deliver them to (pinned) host memory [n,3,H,W]; the copy of view k
+        overlaps the render of view k+1.  Returns (out_host, num_rendered[n])."""
+        cams = pack_cameras(cameras)
+        n = cams.shape[0]
+        if out_host is None:
+            out_host = torch.empty((n, 3, self.height, self.width), dtype=torch.float32).pin_memory()
+        nr = (C.c_int * max(n, 1))()
+        rc = _lib.lib().gsr_renderer_render_host(self._h, cams.ctypes.data, n, float(tan_fovx), float(tan_fovy),
+                                                 out_host.data_ptr(), C.cast(nr, C.c_void_p))
+        _lib.check(rc)
+        return out_host, [int(nr[i]) for i in range(n)]
+
+
+def gather_frames(local_frames: torch.Tensor, n_views: int, rank: int, world_size: int, dst: int = 0, group=None):
+    """Bring the frames of a round-robin-sharded batch to `dst` in view order.
+
+    local_frames: [len(shard_views(n_views, rank, world_size)), 3, H, W] on this rank.
+    Returns [n_views,3,H,W] on dst, None elsewhere.  One torch.distributed gather (NCCL on GPU
+    ranks, gloo on CPU); shards are padded to views_per_rank so every rank sends the same size."""
+    import torch.distributed as dist
+
+    per = views_per_rank(n_views, world_size)
+    shape = (per,) + tuple(local_frames.shape[1:])
+    send = local_frames
+    if local_frames.shape[0] != per:
+        send = torch.zeros(shape, dtype=local_frames.dtype, device=local_frames.device)
+        send[: local_frames.shape[0]] = local_frames
+    send = send.contiguous()
+    if world_size == 1:
+        return send[:n_views]
+    recv = [torch.empty_like(send) for _ in range(world_size)] if rank == dst else None
+    dist.gather(send, recv, dst=dst, group=group)
+    if rank != dst:
+        return None
+    out = torch.empty((n_views,) + tuple(local_frames.shape[1:]), dtype=local_frames.dtype,
+                      device=local_frames.device)
+    for r in range(world_size):
+        idx = shard_views(n_views, r, world_size)
+        if idx:
+            out[idx] = recv[r][: len(idx)]
+    return out

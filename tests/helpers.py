@@ -1,0 +1,109 @@
+"""Shared helpers for the parity tests: run the CUDA path (through the C ABI) and the CPU
+oracle on the same seeded scene and camera."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def run_cuda(scene, cam, *, compat=False, use_rects=False, D=None, flags=0, background=(0.0, 0.0, 0.0),
+             cov3D_precomp=None, boxmin=None, boxmax=None, radii_external=False, timings=False, device="cuda"):
+    """Returns dict with num_rendered + every scratch field as numpy arrays."""
+    import torch
+
+    from gsrast_b200 import rasterizer as R
+
+    dev = torch.device(device)
+    t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    W, H = cam.width, cam.height
+    geom, binning, img = R.resize_functional(dev), R.resize_functional(dev), R.resize_functional(dev)
+    out_color = torch.full((3, H, W), -7.0, dtype=torch.float32, device=dev)  # sentinel: must be overwritten
+    bg = t(np.asarray(background, np.float32))
+    view, proj, cpos = t(cam.viewmatrix), t(cam.projmatrix), t(cam.cam_pos)
+    P = scene.P
+    rects = torch.zeros((max(P, 1), 2), dtype=torch.int32, device=dev) if use_rects else None
+    radii = torch.full((max(P, 1),), -1, dtype=torch.int32, device=dev) if radii_external else None
+    if compat:
+        means4, scales4, rot, opac, shs_raw = scene.gsrast_layout()
+        keep = [t(means4), t(shs_raw), t(opac), t(scales4), t(rot), t(scene.colors_precomp), t(cov3D_precomp)]
+        res = R.gscuda_forward(geom, binning, img, P, 3, 16, bg, W, H, keep[0], keep[1], keep[5], keep[2], keep[3],
+                               1.0, keep[4], keep[6], view, proj, cpos, cam.tan_fovx, cam.tan_fovy, False, out_color,
+                               radii, rects, boxmin, boxmax, flags=flags, timings=timings)
+    else:
+        keep = [t(scene.means3D), t(scene.shs), t(scene.opacities), t(scene.scales), t(scene.rotations),
+                t(scene.colors_precomp), t(cov3D_precomp)]
+        res = R.Rasterizer.forward(geom, binning, img, P, scene.sh_degree if D is None else D,
+                                   max(scene.max_coeffs, 1), bg, W, H, keep[0], keep[1], keep[5], keep[2], keep[3],
+                                   1.0, keep[4], keep[6], view, proj, cpos, cam.tan_fovx, cam.tan_fovy, False,
+                                   out_color, radii, rects, boxmin, boxmax, flags=flags, timings=timings)
+    torch.cuda.synchronize()
+    times = None
+    if timings:
+        res, times = res
+    Rn = int(res)
+    out = dict(num_rendered=Rn, times=times, allocs=(geom, binning, img))
+    g = R.GeometryState.from_chunk(geom.buf, P) if P > 0 else {}
+    for k, v in g.items():
+        out[k] = v.cpu().numpy()
+    if "tiles_touched" in out:
+        out["tiles_touched"] = out["tiles_touched"].view(np.uint32)
+        out["point_offsets"] = out["point_offsets"].view(np.uint32)
+    out["radii"] = radii.cpu().numpy()[:P] if radii_external else out.get("internal_radii")
+    out["rects"] = rects.cpu().numpy()[:P] if use_rects else None
+    im = R.ImageState.from_chunk(img.buf, W, H)
+    out["ranges"] = im["ranges"].cpu().numpy().view(np.uint32)
+    out["n_contrib"] = im["n_contrib"].cpu().numpy().view(np.uint32)
+    out["final_T"] = im["accum_alpha"].cpu().numpy()
+    if Rn > 0:
+        b = R.BinningState.from_chunk(binning.buf, Rn)
+        out["keys"] = b["point_list_keys"].cpu().numpy().view(np.uint64)
+        out["values"] = b["point_list"].cpu().numpy().view(np.uint32)
+    else:
+        out["keys"] = np.zeros(0, np.uint64)
+        out["values"] = np.zeros(0, np.uint32)
+    out["out_color"] = out_color.cpu().numpy()
+    return out
+
+
+def run_oracle(oracle, scene, cam, *, compat=False, use_rects=False, D=None, background=(0.0, 0.0, 0.0),
+               cov3D_precomp=None, boxmin=None, boxmax=None, out_color_init=None):
+    mode = oracle.MODE_GSRAST if compat else oracle.MODE_CONTRACT
+    if cov3D_precomp is None and boxmin is None and boxmax is None:
+        return oracle.forward_scene(scene, cam, background=background, D=D, use_rects=use_rects, mode=mode,
+                                    out_color_init=out_color_init)
+    assert not compat
+    return oracle.forward(P=scene.P, D=scene.sh_degree if D is None else D, M=scene.max_coeffs,
+                          background=np.asarray(background, np.float32), W=cam.width, H=cam.height,
+                          means3D=scene.means3D, shs=scene.shs, colors_precomp=scene.colors_precomp,
+                          opacities=scene.opacities, scales=scene.scales, scale_modifier=1.0,
+                          rotations=scene.rotations, cov3D_precomp=cov3D_precomp, viewmatrix=cam.viewmatrix,
+                          projmatrix=cam.projmatrix, cam_pos=cam.cam_pos, tan_fovx=cam.tan_fovx,
+                          tan_fovy=cam.tan_fovy, use_rects=use_rects, boxmin=boxmin, boxmax=boxmax, mode=mode)
+
+
+def psnr(a, b):
+    mse = float(np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2))
+    return 99.0 if mse == 0 else 10.0 * np.log10(1.0 / mse)
+
+
+def assert_parity(cu, ref, *, colours_from_sh=True, check_image=True, n_contrib_budget=2e-4):
+    """Bit-exact: radii, tiles_touched, point_offsets, sorted keys/values, ranges (and the
+    float scratch of visible Gaussians).  Image: max-abs <= 1/255, PSNR >= 50 dB."""
+    assert cu["num_rendered"] == ref.num_rendered
+    assert np.array_equal(cu["radii"], ref.radii), "radii"
+    assert np.array_equal(cu["tiles_touched"], ref.tiles_touched), "tiles_touched"
+    assert np.array_equal(cu["point_offsets"], ref.point_offsets), "point_offsets"
+    vis = ref.radii > 0
+    for name in ("depths", "means2D", "conic_opacity"):
+        assert np.array_equal(cu[name][vis].view(np.uint32), ref[name][vis].view(np.uint32)), name
+    if colours_from_sh:
+        assert np.array_equal(cu["rgb"][vis].view(np.uint32), ref.rgb[vis].view(np.uint32)), "rgb"
+    assert np.array_equal(cu["keys"], ref["keys"]), "sorted keys"
+    assert np.array_equal(cu["values"], ref["values"]), "sorted values"
+    assert np.array_equal(cu["ranges"], ref.ranges), "tile ranges"
+    if check_image and ref.num_rendered > 0:
+        err = np.abs(cu["out_color"] - ref.out_color)
+        assert err.max() <= 1.0 / 255.0, "image max-abs %.3e" % err.max()
+        assert psnr(cu["out_color"], ref.out_color) >= 50.0
+        assert np.abs(cu["final_T"] - ref.final_T).max() <= 1.0 / 255.0
+        bad = float(np.mean(cu["n_contrib"] != ref.n_contrib))
+        assert bad <= n_contrib_budget, "n_contrib mismatch fraction %.2e" % bad

@@ -1,0 +1,74 @@
+"""View-batch renderer (gsr_renderer_*, the C form of GSGaussians) and the viewer-buffer repack."""
+import numpy as np
+import pytest
+
+from gsrast_b200 import camera as Cm
+from gsrast_b200 import scene as S
+
+from helpers import run_cuda
+
+pytestmark = pytest.mark.gpu
+
+
+def test_view_batch_matches_single_forward():
+    import torch
+
+    from gsrast_b200.views import ViewRenderer
+
+    sc = S.make_config_scene("C2", P=60_000)[0]
+    W, H = 800, 448
+    cams = Cm.orbit_cameras(5, W, H)
+    vr = ViewRenderer.from_scene(sc, W, H)
+    out, nr = vr.render(cams, cams[0].tan_fovx, cams[0].tan_fovy)
+    torch.cuda.synchronize()
+    host, nr_h = vr.render_host(cams, cams[0].tan_fovx, cams[0].tan_fovy)
+    assert nr == nr_h
+    for v, cam in enumerate(cams):
+        single = run_cuda(sc, cam)
+        assert single["num_rendered"] == nr[v]
+        assert np.array_equal(out[v].cpu().numpy(), single["out_color"])
+        assert np.array_equal(host[v].numpy(), single["out_color"])
+    out2, nr2, times = vr.render(cams[:2], cams[0].tan_fovx, cams[0].tan_fovy, timings=True)
+    assert times["num_rendered"] == nr2[1] and times["sort_passes"] >= 5 and times["kernel_launches"] >= 10
+    assert times["total_ms"] > 0
+    vr.close()
+
+
+def test_view_batch_compat_mode():
+    import torch
+
+    from gsrast_b200.views import ViewRenderer
+
+    sc = S.make_config_scene("C1", P=30_000)[0]
+    W, H = 640, 360
+    cam = Cm.default_camera(W, H)
+    means4, scales4, rot, opac, shs_raw = sc.gsrast_layout()
+    t = lambda a: torch.from_numpy(a).cuda()  # noqa: E731
+    vr = ViewRenderer(P=sc.P, D=3, M=16, means3D=t(means4), shs=t(shs_raw), colors_precomp=None, opacities=t(opac),
+                      scales=t(scales4), rotations=t(rot), background=torch.zeros(3, device="cuda"), width=W, height=H,
+                      compat=True)
+    out, nr = vr.render([cam], cam.tan_fovx, cam.tan_fovy)
+    torch.cuda.synchronize()
+    single = run_cuda(sc, cam, compat=True)
+    assert nr[0] == single["num_rendered"] and np.array_equal(out[0].cpu().numpy(), single["out_color"])
+
+
+def test_repack_gsrast_scene():
+    """vec4 / raw-PLY viewer buffers -> contract layout on the device."""
+    import torch
+
+    from gsrast_b200 import _lib
+
+    sc = S.make_config_scene("C1", P=10_001)[0]
+    means4, scales4, rot, opac, shs_raw = sc.gsrast_layout()
+    t = lambda a: torch.from_numpy(a).cuda()  # noqa: E731
+    m4, s4, raw = t(means4), t(scales4), t(shs_raw)
+    m3 = torch.empty((sc.P, 3), device="cuda")
+    s3 = torch.empty((sc.P, 3), device="cuda")
+    sh = torch.empty((sc.P, 16, 3), device="cuda")
+    _lib.check(_lib.lib().gsr_repack_gsrast_scene(sc.P, m4.data_ptr(), s4.data_ptr(), raw.data_ptr(), m3.data_ptr(),
+                                                  s3.data_ptr(), sh.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert np.array_equal(m3.cpu().numpy(), sc.means3D)
+    assert np.array_equal(s3.cpu().numpy(), sc.scales)
+    assert np.array_equal(sh.cpu().numpy(), sc.shs)

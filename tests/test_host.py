@@ -1,0 +1,117 @@
+"""Host-side logic on CPU: camera conventions, synthetic scenes, the 62-float PLY, view
+sharding and the frame gather (gloo, world_size 2)."""
+import math
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+
+from gsrast_b200 import camera as Cm
+from gsrast_b200 import scene as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_camera_matches_gsrast_conventions():
+    cam = Cm.default_camera(1920, 1080)
+    v = cam.viewmatrix.reshape(4, 4)  # [col,row]
+    # eye (0,0,-5) looking at the origin: view-space z of the origin is +5 after the row-2 flip
+    p = np.array([0, 0, 0, 1], np.float32)
+    pv = np.einsum("cr,c->r", v, p)
+    assert pv[2] == np.float32(5.0)
+    # proj = perspective * (unflipped) view: clip w = distance along the view axis
+    ph = np.einsum("cr,c->r", cam.projmatrix.reshape(4, 4), p)
+    assert abs(ph[3] - 5.0) < 1e-6 and abs(ph[0]) < 1e-6 and abs(ph[1]) < 1e-6
+    assert cam.tan_fovy == np.float32(math.tan(math.radians(45) / 2))
+    assert abs(cam.tan_fovx - cam.tan_fovy * 1920 / 1080) < 1e-6
+    # invertUp: world +y maps to +y_ndc * (-1) ... i.e. image rows grow along world +y? check sign consistency
+    up = np.einsum("cr,c->r", cam.projmatrix.reshape(4, 4), np.array([0, 1, 0, 1], np.float32))
+    assert up[1] < 0  # up vector (0,-1,0): world +y points down the image
+
+
+def test_scene_generator_is_seeded_and_shaped():
+    a, cfg = S.make_config_scene("C1", P=5000)
+    b, _ = S.make_config_scene("C1", P=5000)
+    assert np.array_equal(a.means3D, b.means3D) and np.array_equal(a.shs, b.shs)
+    assert a.means3D.shape == (5000, 3) and a.shs.shape == (5000, 16, 3) and a.rotations.shape == (5000, 4)
+    assert np.allclose(np.linalg.norm(a.rotations, axis=1), 1, atol=1e-5)
+    assert 0 < a.opacities.min() and a.opacities.max() < 1
+    assert np.linalg.norm(a.means3D, axis=1).max() < 3.6
+    c5, _ = S.make_config_scene("C5", P=1000)
+    assert c5.shs is None and c5.colors_precomp.shape == (1000, 3) and c5.opacities.mean() < 0.15
+    for name in ("C1", "C2", "C3", "C4", "C5"):
+        assert name in S.CONFIGS
+
+
+def test_ply_round_trip(tmp_path):
+    sc, _ = S.make_config_scene("C1", P=777)
+    path = str(tmp_path / "data.ply")
+    S.write_ply(path, sc)
+    assert os.path.getsize(path) > 777 * 62 * 4
+    back = S.read_ply(path)
+    assert back.P == 777
+    assert np.array_equal(back.means3D, sc.means3D) and np.array_equal(back.shs, sc.shs)
+    assert np.allclose(back.scales, sc.scales, rtol=1e-6) and np.allclose(back.opacities, sc.opacities, atol=1e-6)
+    assert np.allclose(back.rotations, sc.rotations, atol=1e-6)
+    # PLY order <-> contract order (the SH layout trap)
+    raw = S.contract_sh_to_ply_order(sc.shs)
+    assert raw[5, 3 + 1 * 15 + (4 - 1)] == sc.shs[5, 4, 1]
+    assert np.array_equal(S.ply_order_to_contract_sh(raw), sc.shs)
+
+
+def test_shard_views_partition():
+    from gsrast_b200.views import shard_views, views_per_rank
+
+    for n in (0, 1, 7, 256):
+        for w in (1, 2, 4, 8):
+            parts = [shard_views(n, r, w) for r in range(w)]
+            assert sorted(sum(parts, [])) == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+            assert max(len(p) for p in parts) <= views_per_rank(n, w) if n else True
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from gsrast_b200.views import shard_views, gather_frames
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank, n = dist.get_rank(), 5
+mine = shard_views(n, rank, 2)
+local = torch.stack([torch.full((3, 4, 6), float(v)) for v in mine])
+out = gather_frames(local, n, rank, 2, dst=0)
+if rank == 0:
+    assert out.shape == (5, 3, 4, 6)
+    assert [float(out[v, 0, 0, 0]) for v in range(5)] == [0.0, 1.0, 2.0, 3.0, 4.0]
+    print("GATHER_OK")
+else:
+    assert out is None
+dist.destroy_process_group()
+'''
+
+
+def test_gather_frames_gloo_world2(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "GATHER_OK" in outs[0]
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """bench.py --impl reference times the CPU implementation and prints the contract's JSON line."""
+    import json
+
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                                   "--warmup", "0", "--workload", "C1"], timeout=600).decode()
+    line = json.loads(out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgsrast_b200.so")
+# GSRAST_B200_LIB selects an alternative build of the same library (A/B runs of kernel variants)
+LIB_PATH = os.environ.get("GSRAST_B200_LIB") or os.path.join(_HERE, "libgsrast_b200.so")
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_void_p)
 

@@ -69,10 +69,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(uint32_t*
 
 __device__ __forceinline__ void get_rect_dev(float px, float py, int ex, int ey, int gx, int gy, int& minx, int& miny,
                                              int& maxx, int& maxy) {
-    minx = min(gx, max(0, __float2int_rz(fdiv(fsub(px, (float)ex), (float)TILE_X))));
-    miny = min(gy, max(0, __float2int_rz(fdiv(fsub(py, (float)ey), (float)TILE_Y))));
-    maxx = min(gx, max(0, __float2int_rz(fdiv(fsub(fadd(fadd(px, (float)ex), (float)TILE_X), 1.0f), (float)TILE_X))));
-    maxy = min(gy, max(0, __float2int_rz(fdiv(fsub(fadd(fadd(py, (float)ey), (float)TILE_Y), 1.0f), (float)TILE_Y))));
+    // x / 16.0f == x * 0.0625f bit for bit (exact power-of-two scaling)
+    minx = min(gx, max(0, __float2int_rz(fmul(fsub(px, (float)ex), 1.0f / TILE_X))));
+    miny = min(gy, max(0, __float2int_rz(fmul(fsub(py, (float)ey), 1.0f / TILE_Y))));
+    maxx = min(gx, max(0, __float2int_rz(fmul(fsub(fadd(fadd(px, (float)ex), (float)TILE_X), 1.0f), 1.0f / TILE_X))));
+    maxy = min(gy, max(0, __float2int_rz(fmul(fsub(fadd(fadd(py, (float)ey), (float)TILE_Y), 1.0f), 1.0f / TILE_Y))));
 }
 
 // One block = the same 256 Gaussians as in preprocess.
@@ -153,23 +154,40 @@ __global__ void __launch_bounds__(PRE_THREADS) duplicate_kernel(
     }
 }
 
+// Four consecutive sorted keys per thread (two 16-byte loads + the left neighbour): boundary
+// detection in the tile-id half of the key.  ranges[] must be zeroed beforehand.
 template <bool COMPAT>
 __global__ void __launch_bounds__(256) identify_ranges_kernel(const size_t n, const uint64_t* __restrict__ keys,
                                                               uint2* __restrict__ ranges) {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
-    const uint32_t cur = (uint32_t)(keys[idx] >> 32);
-    if (idx == 0) {
-        ranges[cur].x = 0;
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 >= n) return;
+    uint64_t k[4];
+    if (i0 + 3 < n) {
+        const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2*>(keys + i0));
+        const ulonglong2 b = __ldg(reinterpret_cast<const ulonglong2*>(keys + i0 + 2));
+        k[0] = a.x; k[1] = a.y; k[2] = b.x; k[3] = b.y;
     } else {
-        const uint32_t prev = (uint32_t)(keys[idx - 1] >> 32);
-        if (prev != cur) {
-            ranges[prev].y = (uint32_t)idx;
-            ranges[cur].x = (uint32_t)idx;
-        }
-        if (COMPAT && idx == n - 1) ranges[cur].y = (uint32_t)n;  // GSCuda.cu:533-536 (inside the else)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) k[j] = (i0 + j < n) ? __ldg(keys + i0 + j) : 0ull;
     }
-    if (!COMPAT && idx == n - 1) ranges[cur].y = (uint32_t)n;
+    uint32_t prev = (i0 > 0) ? (uint32_t)(__ldg(keys + i0 - 1) >> 32) : 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const size_t idx = i0 + j;
+        if (idx >= n) break;
+        const uint32_t cur = (uint32_t)(k[j] >> 32);
+        if (idx == 0) {
+            ranges[cur].x = 0;
+        } else {
+            if (prev != cur) {
+                ranges[prev].y = (uint32_t)idx;
+                ranges[cur].x = (uint32_t)idx;
+            }
+            if (COMPAT && idx == n - 1) ranges[cur].y = (uint32_t)n;  // GSCuda.cu:533-536 (inside the else)
+        }
+        if (!COMPAT && idx == n - 1) ranges[cur].y = (uint32_t)n;
+        prev = cur;
+    }
 }
 
 }  // namespace
@@ -199,7 +217,7 @@ int launch_identify_ranges(const uint64_t* keys, size_t n, uint32_t* ranges, int
     cudaError_t e = cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)num_tiles, s);
     if (e != cudaSuccess) return -(int)e;
     if (n == 0) return 0;
-    const unsigned blocks = (unsigned)((n + 255) / 256);
+    const unsigned blocks = (unsigned)((n + 1023) / 1024);
     if (compat)
         identify_ranges_kernel<true><<<blocks, 256, 0, s>>>(n, keys, reinterpret_cast<uint2*>(ranges));
     else

@@ -29,10 +29,11 @@ __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterp
 // getRect (GSCuda.cu:237-259): tile-space AABB, truncation toward zero, clamped to the grid.
 __device__ __forceinline__ void get_rect(float px, float py, int ex, int ey, int gx, int gy, int& minx, int& miny,
                                          int& maxx, int& maxy) {
-    minx = min(gx, max(0, __float2int_rz(fdiv(fsub(px, (float)ex), (float)TILE_X))));
-    miny = min(gy, max(0, __float2int_rz(fdiv(fsub(py, (float)ey), (float)TILE_Y))));
-    maxx = min(gx, max(0, __float2int_rz(fdiv(fsub(fadd(fadd(px, (float)ex), (float)TILE_X), 1.0f), (float)TILE_X))));
-    maxy = min(gy, max(0, __float2int_rz(fdiv(fsub(fadd(fadd(py, (float)ey), (float)TILE_Y), 1.0f), (float)TILE_Y))));
+    // x / 16.0f == x * 0.0625f bit for bit (exact power-of-two scaling)
+    minx = min(gx, max(0, __float2int_rz(fmul(fsub(px, (float)ex), 1.0f / TILE_X))));
+    miny = min(gy, max(0, __float2int_rz(fmul(fsub(py, (float)ey), 1.0f / TILE_Y))));
+    maxx = min(gx, max(0, __float2int_rz(fmul(fsub(fadd(fadd(px, (float)ex), (float)TILE_X), 1.0f), 1.0f / TILE_X))));
+    maxy = min(gy, max(0, __float2int_rz(fmul(fsub(fadd(fadd(py, (float)ey), (float)TILE_Y), 1.0f), 1.0f / TILE_Y))));
 }
 
 // upstream ndc2Pix: ((v + 1.0) * S - 1.0) * 0.5 evaluated in double, rounded to float once.

@@ -35,6 +35,13 @@ constexpr int SORT_ITEMS = 16;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 pairs
 constexpr int MAX_PASSES = 8;
+#ifndef GSR_LOOKBACK_W
+#define GSR_LOOKBACK_W 8
+#endif
+#ifndef GSR_SORT_MIN_BLOCKS
+#define GSR_SORT_MIN_BLOCKS 3
+#endif
+constexpr int LOOKBACK_W = GSR_LOOKBACK_W;
 
 constexpr uint32_t FLAG_AGG = 1u << 30;
 constexpr uint32_t FLAG_INC = 2u << 30;
@@ -53,46 +60,42 @@ struct SortTemp {
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ---- up-front histograms of every digit place -------------------------------------------
-// Warp-private counter rows, updated by the leader of each match.any group with plain
-// loads/stores (the rows are private to the warp, so no atomics are needed).
+// Block-shared counters updated with shared-memory atomics: measured on B200 (tools/microbench.cu)
+// at ~2.4 SM-cycles per warp-wide ATOMS against ~60 for match.any and ~25 for an 8-step ballot
+// match, so plain atomics are the right tool for an order-independent count.
 template <int PASSES>
 __global__ void __launch_bounds__(HIST_THREADS) histogram_kernel(const uint64_t* __restrict__ keys, const size_t n,
                                                                  const int end_bit, uint32_t* __restrict__ hist) {
-    extern __shared__ uint32_t s_hist[];  // [HIST_WARPS][PASSES][RADIX]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < HIST_WARPS * PASSES * RADIX; i += HIST_THREADS) s_hist[i] = 0;
+    __shared__ uint32_t s_hist[PASSES * RADIX];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < PASSES * RADIX; i += HIST_THREADS) s_hist[i] = 0;
     __syncthreads();
-    uint32_t* my = s_hist + warp * PASSES * RADIX;
 
-    const size_t per_block = (size_t)HIST_THREADS * 8;
+    constexpr int PER_THREAD = 8;
+    const size_t per_block = (size_t)HIST_THREADS * PER_THREAD;
     for (size_t base = (size_t)blockIdx.x * per_block; base < n; base += (size_t)gridDim.x * per_block) {
-        uint64_t k[8];
-        bool ok[8];
+        uint64_t k[PER_THREAD];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < PER_THREAD; ++i) {
             const size_t pos = base + (size_t)i * HIST_THREADS + tid;
-            ok[i] = pos < n;
-            k[i] = ok[i] ? __ldg(keys + pos) : 0ull;
+            k[i] = pos < n ? __ldg(keys + pos) : 0ull;
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < PER_THREAD; ++i) {
+            if (base + (size_t)i * HIST_THREADS + tid < n) {
 #pragma unroll
-            for (int ps = 0; ps < PASSES; ++ps) {
-                const int shift = ps * RADIX_BITS;
-                const int nb = min(RADIX_BITS, end_bit - shift);
-                const uint32_t d = ok[i] ? (uint32_t)((k[i] >> shift) & ((1u << nb) - 1u)) : (0x100u | lane);
-                const unsigned peers = __match_any_sync(0xffffffffu, d);
-                if (ok[i] && lane == (__ffs(peers) - 1)) my[ps * RADIX + d] += __popc(peers);
+                for (int ps = 0; ps < PASSES; ++ps) {
+                    const int shift = ps * RADIX_BITS;
+                    const int nb = min(RADIX_BITS, end_bit - shift);
+                    atomicAdd(&s_hist[ps * RADIX + (uint32_t)((k[i] >> shift) & ((1u << nb) - 1u))], 1u);
+                }
             }
-            __syncwarp();
         }
     }
     __syncthreads();
     for (int i = tid; i < PASSES * RADIX; i += HIST_THREADS) {
-        uint32_t s = 0;
-#pragma unroll
-        for (int w = 0; w < HIST_WARPS; ++w) s += s_hist[w * PASSES * RADIX + i];
-        if (s) atomicAdd(hist + i, s);
+        const uint32_t c = s_hist[i];
+        if (c) atomicAdd(hist + i, c);
     }
 }
 
@@ -119,117 +122,99 @@ __global__ void __launch_bounds__(RADIX) scan_histograms_kernel(uint32_t* __rest
     }
 }
 
+// Status words carry flag and count in ONE 32-bit word, so relaxed gpu-scope accesses suffice.
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
     uint32_t v;
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
-    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // ---- one digit pass ------------------------------------------------------------------------
-__global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(
-    const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out,
-    uint32_t* __restrict__ vals_out, const size_t n, const int shift, const int nbits,
-    const uint32_t* __restrict__ digit_offsets,  // [RADIX] exclusive offsets of this pass
-    uint32_t* __restrict__ status,               // [num_tiles][RADIX], zero-initialised
-    uint32_t* __restrict__ ticket, uint32_t* __restrict__ error_flag) {
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    uint64_t* s_keys = reinterpret_cast<uint64_t*>(s_raw);                                // [SORT_TILE]
-    uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_raw + (size_t)SORT_TILE * 8);        // [SORT_TILE]
-    uint32_t* s_whist = reinterpret_cast<uint32_t*>(s_raw + (size_t)SORT_TILE * 12);      // [SORT_WARPS][RADIX]
-    uint32_t* s_block_off = s_whist + SORT_WARPS * RADIX;                                 // [RADIX]
-    uint32_t* s_global = s_block_off + RADIX;                                             // [RADIX]
-    uint32_t* s_misc = s_global + RADIX;                                                  // [16]
+// Shared memory: [SORT_TILE] u64 key staging (re-used as u32 for the values) | [SORT_TILE] u32 value
+// prefetch (cp.async) | per-warp digit counters [SORT_WARPS][RADIX] | per-warp match masks
+// [SORT_WARPS][RADIX] | global bases [RADIX] | misc.
+constexpr size_t ONESWEEP_SMEM = (size_t)SORT_TILE * 12 + (size_t)(2 * SORT_WARPS * RADIX + RADIX + 16) * 4;
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// The digit of a pass never straddles the two 32-bit halves of the key (shift is a multiple of 8 and
+// the digit has <= 8 bits), so all digit arithmetic is 32-bit: pick the half, shift, mask.
+__device__ __forceinline__ uint32_t digit_of(const uint2 k, const bool hi, const int sh, const uint32_t dmask) {
+    return ((hi ? k.y : k.x) >> sh) & dmask;
+}
+
+template <bool FULL>
+__device__ __forceinline__ void onesweep_tile(const uint2* __restrict__ kin, const uint32_t* __restrict__ vin,
+                                              uint2* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                              const uint32_t n_tile, const uint32_t tile, const bool hi, const int sh,
+                                              const uint32_t dmask, const uint32_t* __restrict__ digit_offsets,
+                                              uint32_t* __restrict__ status, uint32_t* __restrict__ error_flag,
+                                              const bool vec_vals, unsigned char* s_raw) {
+    uint2* s_keys = reinterpret_cast<uint2*>(s_raw);                                  // [SORT_TILE]
+    uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_raw);                            // aliases s_keys
+    uint32_t* s_vpre = reinterpret_cast<uint32_t*>(s_raw + (size_t)SORT_TILE * 8);    // [SORT_TILE]
+    uint32_t* s_whist = s_vpre + SORT_TILE;                                           // [SORT_WARPS][RADIX]
+    uint32_t* s_global = s_whist + 2 * SORT_WARPS * RADIX;                            // [RADIX]
+    uint32_t* s_misc = s_global + RADIX;                                              // [16]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_misc[0] = atomicAdd(ticket, 1u);
-    for (int i = tid; i < SORT_WARPS * RADIX; i += SORT_THREADS) s_whist[i] = 0;
-    __syncthreads();
-    const uint32_t tile = s_misc[0];
-    const size_t tile_base = (size_t)tile * SORT_TILE;
-    const uint32_t n_tile = (uint32_t)min((size_t)SORT_TILE, n - tile_base);
-    const uint32_t dmask = (1u << nbits) - 1u;
-
-    // 1. warp-striped load: item i of this thread sits at warp_base + i*32 + lane
-    uint64_t key[SORT_ITEMS];
-    uint32_t val[SORT_ITEMS];
     const uint32_t warp_base = warp * (32 * SORT_ITEMS);
+    uint32_t* my_hist = s_whist + warp * RADIX;  // my_mask = my_hist + SORT_WARPS*RADIX
+
+    // 0. values: asynchronous prefetch straight into shared memory (no registers held)
+    if (FULL && vec_vals) {
+#pragma unroll
+        for (int c = 0; c < SORT_TILE / 4 / SORT_THREADS; ++c) {
+            const int ch = tid + c * SORT_THREADS;
+            cp_async_16(s_vpre + ch * 4, vin + ch * 4);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < SORT_ITEMS; ++i) {
+            const uint32_t loc = tid + i * SORT_THREADS;
+            if (loc < n_tile) cp_async_4(s_vpre + loc, vin + loc);
+        }
+    }
+
+    // 1. warp-striped key load (item i of this thread sits at warp_base + i*32 + lane) + early counts
+    uint2 key[SORT_ITEMS];
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; ++i) {
         const uint32_t loc = warp_base + i * 32 + lane;
-        if (loc < n_tile) {
-            key[i] = keys_in[tile_base + loc];
-            val[i] = vals_in[tile_base + loc];
-        } else {
-            key[i] = ~0ull;
-            val[i] = 0;
-        }
+        key[i] = (FULL || loc < n_tile) ? __ldg(kin + loc) : make_uint2(~0u, ~0u);
     }
-
-    // 2. rank inside the warp, in item order (i major, lane minor) -> stable
-    uint32_t* my_hist = s_whist + warp * RADIX;
-    uint32_t rank[SORT_ITEMS];
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; ++i) {
-        const bool ok = (warp_base + i * 32 + lane) < n_tile;
-        const uint32_t d = ok ? ((uint32_t)(key[i] >> shift) & dmask) : (0x100u | lane);
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        const int leader = __ffs(peers) - 1;
-        uint32_t base = 0;
-        if (ok && lane == leader) {
-            base = my_hist[d];
-            my_hist[d] = base + __popc(peers);
-        }
-        base = __shfl_sync(0xffffffffu, base, leader);
-        rank[i] = base + __popc(peers & ((1u << lane) - 1u));
-        __syncwarp();
+        if (FULL || (warp_base + i * 32 + lane) < n_tile) atomicAdd(&my_hist[digit_of(key[i], hi, sh, dmask)], 1u);
     }
     __syncthreads();
 
-    // 3. thread d: exclusive prefix of digit d over the warps, tile count of digit d
+    // 2. thread d: tile count of digit d, published at once; exclusive scan over digits; per-warp
+    //    start offsets of digit d inside the tile's staging order
     uint32_t bins = 0;
-    {
 #pragma unroll
-        for (int w = 0; w < SORT_WARPS; ++w) {
-            const uint32_t c = s_whist[w * RADIX + tid];
-            s_whist[w * RADIX + tid] = bins;
-            bins += c;
-        }
+    for (int w = 0; w < SORT_WARPS; ++w) bins += s_whist[w * RADIX + tid];
+    uint32_t* my_status = status + (size_t)tile * RADIX + tid;
+    st_volatile_u32(my_status, (tile == 0 ? FLAG_INC : FLAG_AGG) | bins);
+    // first look-back window: these loads fly while the block ranks
+    uint32_t look[LOOKBACK_W];
+#pragma unroll
+    for (int w = 0; w < LOOKBACK_W; ++w) {
+        const int64_t tw = (int64_t)tile - 1 - w;
+        look[w] = (tw >= 0) ? ld_volatile_u32(status + (size_t)tw * RADIX + tid) : FLAG_INC;
     }
-
-    // 4. decoupled look-back for digit `tid`
-    {
-        uint32_t* my_status = status + (size_t)tile * RADIX + tid;
-        uint32_t excl = 0;
-        if (tile == 0) {
-            st_volatile_u32(my_status, FLAG_INC | bins);
-        } else {
-            st_volatile_u32(my_status, FLAG_AGG | bins);
-            int64_t t = (int64_t)tile - 1;
-            uint32_t spins = 0;
-            while (true) {
-                const uint32_t v = ld_volatile_u32(status + (size_t)t * RADIX + tid);
-                const uint32_t f = v & FLAG_MASK;
-                if (f == 0) {
-                    if (++spins > (1u << 22)) {  // watchdog: never expected to trip
-                        atomicExch(error_flag, 1u);
-                        break;
-                    }
-                    __nanosleep(40);
-                    continue;
-                }
-                excl += v & VAL_MASK;
-                if (f == FLAG_INC) break;
-                --t;  // f == FLAG_AGG: keep walking back (tile 0 always publishes FLAG_INC)
-            }
-            st_volatile_u32(my_status, FLAG_INC | ((excl + bins) & VAL_MASK));
-        }
-        s_global[tid] = digit_offsets[tid] + excl;
-    }
-
-    // block-wide exclusive scan of bins over the 256 digits -> position of each digit run in the tile
+    uint32_t block_off;
     {
         uint32_t incl = bins;
 #pragma unroll
@@ -243,33 +228,158 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(
 #pragma unroll
         for (int w = 0; w < SORT_WARPS; ++w)
             if (w < warp) off += s_misc[1 + w];
-        s_block_off[tid] = off + incl - bins;
+        block_off = off + incl - bins;
     }
-    __syncthreads();
-
-    // 5. permute through shared memory into digit order
+    {
+        uint32_t run = block_off;
 #pragma unroll
-    for (int i = 0; i < SORT_ITEMS; ++i) {
-        const bool ok = (warp_base + i * 32 + lane) < n_tile;
-        if (ok) {
-            const uint32_t d = (uint32_t)(key[i] >> shift) & dmask;
-            const uint32_t pos = s_block_off[d] + my_hist[d] + rank[i];
-            s_keys[pos] = key[i];
-            s_vals[pos] = val[i];
+        for (int w = 0; w < SORT_WARPS; ++w) {
+            const uint32_t c = s_whist[w * RADIX + tid];
+            s_whist[w * RADIX + tid] = run;
+            run += c;
         }
     }
     __syncthreads();
-#pragma unroll 4
-    for (uint32_t j = tid; j < n_tile; j += SORT_THREADS) {
-        const uint64_t k = s_keys[j];
-        const uint32_t d = (uint32_t)(k >> shift) & dmask;
-        const size_t g = (size_t)s_global[d] + (j - s_block_off[d]);
-        keys_out[g] = k;
-        vals_out[g] = s_vals[j];
+
+    // 3. stable rank inside the warp, items in order (i major, lane minor).  Peers with the same digit
+    //    find each other through an atomicOr'd lane mask in shared memory; the lowest peer advances the
+    //    warp's running position of that digit and clears the mask.
+    uint32_t pos[SORT_ITEMS];
+    const uint32_t lane_lt = (1u << lane) - 1u;
+#ifdef GSR_DBG_NO_RANK
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) pos[i] = warp_base + i * 32 + lane;
+#else
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        const bool ok = FULL || (warp_base + i * 32 + lane) < n_tile;
+        uint32_t* slot = my_hist + digit_of(key[i], hi, sh, dmask);
+        if (ok) atomicOr(slot + SORT_WARPS * RADIX, 1u << lane);
+        __syncwarp();
+        uint32_t peers = 0, base = 0;
+        if (ok) {
+            peers = slot[SORT_WARPS * RADIX];
+            base = slot[0];
+        }
+        __syncwarp();
+        const uint32_t lower = __popc(peers & lane_lt);
+        if (ok && lower == 0) {
+            slot[0] = base + __popc(peers);
+            slot[SORT_WARPS * RADIX] = 0;
+        }
+        pos[i] = base + lower;
+        __syncwarp();
+    }
+#endif
+
+    // 4. decoupled look-back for digit `tid`, LOOKBACK_W predecessor words per round trip
+    {
+        uint32_t excl = 0;
+#ifdef GSR_DBG_NO_LOOKBACK
+        if (false) {
+#else
+        if (tile != 0) {
+#endif
+            int64_t t = (int64_t)tile - 1;
+            bool done = false;
+            uint32_t spins = 0;
+            while (!done) {
+#pragma unroll
+                for (int w = 0; w < LOOKBACK_W; ++w) {
+                    if (done) break;
+                    uint32_t v = look[w];
+                    while ((v & FLAG_MASK) == 0) {  // predecessor has not published yet
+                        if (++spins > (1u << 22)) {  // watchdog: never expected to trip
+                            atomicExch(error_flag, 1u);
+                            v = FLAG_INC;
+                            break;
+                        }
+                        __nanosleep(32);
+                        v = ld_volatile_u32(status + (size_t)(t - w) * RADIX + tid);
+                    }
+                    excl += v & VAL_MASK;
+                    if ((v & FLAG_MASK) == FLAG_INC) done = true;  // tile 0 always publishes FLAG_INC
+                }
+                if (!done) {
+                    t -= LOOKBACK_W;
+#pragma unroll
+                    for (int w = 0; w < LOOKBACK_W; ++w)
+                        look[w] = (t - w >= 0) ? ld_volatile_u32(status + (size_t)(t - w) * RADIX + tid) : FLAG_INC;
+                }
+            }
+            st_volatile_u32(my_status, FLAG_INC | ((excl + bins) & VAL_MASK));
+        }
+        // global index of staged item j of digit d:  s_global[d] + j
+        s_global[tid] = digit_offsets[tid] + excl - block_off;
+    }
+
+    // 5. keys: permute through shared memory into digit order, write contiguous digit runs
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i)
+        if (FULL || (warp_base + i * 32 + lane) < n_tile) s_keys[pos[i]] = key[i];
+    cp_async_wait_all();
+    __syncthreads();
+    uint32_t gidx[SORT_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; ++k) {
+        const uint32_t j = tid + k * SORT_THREADS;
+        if (FULL || j < n_tile) {
+            const uint2 kk = s_keys[j];
+            const uint32_t g = s_global[digit_of(kk, hi, sh, dmask)] + j;
+            gidx[k] = g;
+#ifdef GSR_DBG_NO_STORE
+            if (g == 0xffffffffu)
+#endif
+            keys_out[g] = kk;
+        }
+    }
+    __syncthreads();
+    // 6. values: same permutation through the same staging buffer
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        const uint32_t loc = warp_base + i * 32 + lane;
+        if (FULL || loc < n_tile) s_vals[pos[i]] = s_vpre[loc];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; ++k) {
+        const uint32_t j = tid + k * SORT_THREADS;
+#ifdef GSR_DBG_NO_STORE
+        if (gidx[k] == 0xffffffffu)
+#endif
+        if (FULL || j < n_tile) vals_out[gidx[k]] = s_vals[j];
     }
 }
 
-constexpr size_t ONESWEEP_SMEM = (size_t)SORT_TILE * 12 + (size_t)(SORT_WARPS * RADIX + RADIX + RADIX + 16) * 4;
+__global__ void __launch_bounds__(SORT_THREADS, GSR_SORT_MIN_BLOCKS) onesweep_kernel(
+    const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out,
+    uint32_t* __restrict__ vals_out, const size_t n, const int shift, const int nbits,
+    const uint32_t* __restrict__ digit_offsets,  // [RADIX] exclusive offsets of this pass
+    uint32_t* __restrict__ status,               // [num_tiles][RADIX], zero-initialised
+    uint32_t* __restrict__ ticket, uint32_t* __restrict__ error_flag, const int vec_vals) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    uint32_t* s_whist = reinterpret_cast<uint32_t*>(s_raw + (size_t)SORT_TILE * 12);
+    uint32_t* s_misc = s_whist + 2 * SORT_WARPS * RADIX + RADIX;
+    const int tid = threadIdx.x;
+    // tiles are handed out in launch order of execution, so a tile only ever waits for tiles that started
+    if (tid == 0) s_misc[0] = atomicAdd(ticket, 1u);
+    for (int i = tid; i < 2 * SORT_WARPS * RADIX; i += SORT_THREADS) s_whist[i] = 0;  // counters + masks
+    __syncthreads();
+    const uint32_t tile = s_misc[0];
+    const size_t tile_base = (size_t)tile * SORT_TILE;
+    const uint32_t n_tile = (uint32_t)min((size_t)SORT_TILE, n - tile_base);
+    const uint2* kin = reinterpret_cast<const uint2*>(keys_in) + tile_base;
+    const uint32_t* vin = vals_in + tile_base;
+    const bool hi = shift >= 32;
+    const int sh = shift & 31;
+    const uint32_t dmask = (1u << nbits) - 1u;
+    if (n_tile == SORT_TILE)
+        onesweep_tile<true>(kin, vin, reinterpret_cast<uint2*>(keys_out), vals_out, n_tile, tile, hi, sh, dmask,
+                            digit_offsets, status, error_flag, vec_vals != 0, s_raw);
+    else
+        onesweep_tile<false>(kin, vin, reinterpret_cast<uint2*>(keys_out), vals_out, n_tile, tile, hi, sh, dmask,
+                             digit_offsets, status, error_flag, vec_vals != 0, s_raw);
+}
 
 size_t num_sort_tiles(size_t n) { return (n + SORT_TILE - 1) / SORT_TILE; }
 
@@ -310,19 +420,13 @@ int launch_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint
         // per-device attributes; cheap enough to set on every call (one process may drive several GPUs)
         GSR_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)ONESWEEP_SMEM));
-        if (passes == 7)
-            GSR_CUDA_TRY(cudaFuncSetAttribute(histogram_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              HIST_WARPS * 7 * RADIX * 4));
-        if (passes == 8)
-            GSR_CUDA_TRY(cudaFuncSetAttribute(histogram_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              HIST_WARPS * 8 * RADIX * 4));
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const size_t per_block = (size_t)HIST_THREADS * 8;
-        const unsigned hblocks = (unsigned)std::min<size_t>((n + per_block - 1) / per_block, (size_t)sms * 4);
+        const unsigned hblocks = (unsigned)std::min<size_t>((n + per_block - 1) / per_block, (size_t)sms * 8);
 #define GSR_HIST(PS) \
-    histogram_kernel<PS><<<hblocks, HIST_THREADS, HIST_WARPS * PS * RADIX * 4, s>>>(keys_a, n, end_bit, hist)
+    histogram_kernel<PS><<<hblocks, HIST_THREADS, 0, s>>>(keys_a, n, end_bit, hist)
         switch (passes) {
             case 1: GSR_HIST(1); break;
             case 2: GSR_HIST(2); break;
@@ -345,7 +449,7 @@ int launch_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint
         const int nbits = std::min(RADIX_BITS, end_bit - shift);
         onesweep_kernel<<<(unsigned)tiles, SORT_THREADS, ONESWEEP_SMEM, s>>>(
             kin, vin, kout, vout, n, shift, nbits, hist + ps * RADIX, status + (size_t)ps * tiles * RADIX, tickets + ps,
-            tickets + MAX_PASSES);
+            tickets + MAX_PASSES, (int)((reinterpret_cast<uintptr_t>(vin) & 15) == 0));
         ++launches;
         if (events) cudaEventRecord(events[2 + ps], s);
         std::swap(kin, kout);

@@ -85,7 +85,7 @@ def psnr(a, b):
     return 99.0 if mse == 0 else 10.0 * np.log10(1.0 / mse)
 
 
-def assert_parity(cu, ref, *, colours_from_sh=True, check_image=True, n_contrib_budget=2e-4):
+def assert_parity(cu, ref, *, colours_from_sh=True, check_image=True, n_contrib_budget=2e-4, colour_max=1.0):
     """Bit-exact: radii, tiles_touched, point_offsets, sorted keys/values, ranges (and the
     float scratch of visible Gaussians).  Image: max-abs <= 1/255, PSNR >= 50 dB."""
     assert cu["num_rendered"] == ref.num_rendered
@@ -102,7 +102,11 @@ def assert_parity(cu, ref, *, colours_from_sh=True, check_image=True, n_contrib_
     assert np.array_equal(cu["ranges"], ref.ranges), "tile ranges"
     if check_image and ref.num_rendered > 0:
         err = np.abs(cu["out_color"] - ref.out_color)
-        assert err.max() <= 1.0 / 255.0, "image max-abs %.3e" % err.max()
+        # 1/255 is the size of ONE alpha-threshold flip for colours in [0,1]; `colour_max` > 1 is only
+        # passed for GSRast-compat scenes whose un-clamped DC colours 0.5+0.4*sh leave that range.
+        tol = max(1.0, colour_max) / 255.0
+        assert err.max() <= tol, "image max-abs %.3e" % err.max()
+        assert float(np.mean(err > 1.0 / 255.0)) <= 1e-5
         assert psnr(cu["out_color"], ref.out_color) >= 50.0
         assert np.abs(cu["final_T"] - ref.final_T).max() <= 1.0 / 255.0
         bad = float(np.mean(cu["n_contrib"] != ref.n_contrib))

@@ -42,8 +42,10 @@ def test_c1_gsrast_compat_parity(oracle, use_rects):
     cam = Cm.default_camera(cfg["W"], cfg["H"])
     cu = run_cuda(sc, cam, compat=True, use_rects=use_rects)
     ref = run_oracle(oracle, sc, cam, compat=True, use_rects=use_rects)
-    assert_parity(cu, ref)
     vis = ref.radii > 0
+    # in-tree colours are 0.5 + 0.4*dc, un-clamped (GSCuda.cu:364-365): with dc ~ N(0,1) they reach ~2.3, so
+    # a single 1/255 alpha-threshold flip moves a pixel by up to |colour|/255
+    assert_parity(cu, ref, colour_max=float(np.abs(ref.rgb[vis]).max()))
     assert np.array_equal(cu["cov3D"][vis].view(np.uint32), ref.cov3D[vis].view(np.uint32))
 
 
@@ -124,7 +126,7 @@ def test_empty_frame_and_empty_scene(oracle):
 
 def test_single_pair_range_quirk(oracle):
     """R == 1: the contract closes the tile range, the in-tree kernel does not (GSCuda.cu:533-536)."""
-    sc = tiny_scene([[0, 0, 0]], scales=[[0.001] * 3])
+    sc = tiny_scene([[0.14, 0, 0]], scales=[[0.001] * 3])  # radius-3 splat strictly inside one tile
     cam = Cm.default_camera(320, 240)
     cu = run_cuda(sc, cam)
     ref = run_oracle(oracle, sc, cam)
@@ -163,7 +165,7 @@ def test_allocator_protocol(oracle):
     assert geom.requests[0] == R.GeometryState.required(sc.P)
     assert img.requests[0] == R.ImageState.required(640, 360)
     assert binning.requests[0] == R.BinningState.required(cu["num_rendered"])
-    g = R.GSGaussians(640, 360)
+    g = R.GSGaussians(640, 360, use_rects=False)
     g.configure_from_splat_data(sc)
     r1 = g.draw(cam)
     p1 = (g._geom.ptr, g._binning.ptr, g._img.ptr)

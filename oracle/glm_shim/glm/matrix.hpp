@@ -1,0 +1,3 @@
+// stand-in header, see glm.hpp
+#pragma once
+#include <glm/glm.hpp>

@@ -4,13 +4,19 @@
 // executed by the product (gsrast_b200/, include/).  Only tests/, the smoke check in
 // __graft_entry__.py and bench.py's cpu_baseline / --impl reference legs may load it.
 //
-// PARITY PINNING STATUS: **parity unpinned** for MODE_CONTRACT — the rasterizer the
-// contract names (graphdeco-inria/diff-gaussian-rasterization @ 59f5f77e, submodule
-// deps/diff-gaussian-rasterization) is an empty directory in /root/reference
-// (.SUBMODULES.json:9-15) and the reference ships no tests, goldens or fixtures
-// (SURVEY.md §4).  MODE_GSRAST restates the in-tree apps/gsrast/gscuda/GSCuda.cu and is
-// pinned against that source compiled unmodified (oracle/_ref, see oracle/Makefile and
-// tests/golden/README.md) when those fixtures are present.
+// PARITY PINNING STATUS
+//   MODE_GSRAST   PINNED.  tests/golden/gsrast_ref_*.npz are outputs of the reference's own in-tree
+//                 rasterizer (apps/gsrast/gscuda/GSCuda.cu compiled unmodified into oracle/_ref and run on
+//                 a B200, see tests/golden/README.md); tests/test_golden.py requires this oracle to match
+//                 them bit for bit (radii, tile counts, offsets, sorted keys/values, ranges, float scratch)
+//                 and the image within tolerance.
+//   MODE_CONTRACT **parity unpinned** — the rasterizer the contract names
+//                 (graphdeco-inria/diff-gaussian-rasterization @ 59f5f77e, submodule
+//                 deps/diff-gaussian-rasterization) is an empty directory in /root/reference
+//                 (.SUBMODULES.json:9-15) and the reference ships no tests, goldens or fixtures for it
+//                 (SURVEY.md §4).  It is restated from SURVEY.md Appendix A; everything the two modes
+//                 share (getRect, scan, key packing, stable sort, ranges, blend loop) is pinned through
+//                 MODE_GSRAST.
 //
 // What it restates (all file:line relative to /root/reference):
 //   forward orchestration        apps/gsrast/gscuda/GSCuda.cu:695-811

@@ -45,15 +45,21 @@ WORKLOADS = {
 }
 
 
-def algorithmic_bytes(P_visible, P_culled, R, tiles, passes, precomp):
-    """SURVEY.md §8(d) per-unit figures."""
+def algorithmic_bytes(P, P_visible, P_culled, R, tiles, depth_passes, tile_passes, precomp):
+    """SURVEY.md §8(d) per-unit figures, plus the bytes the split sort's own launches are defined to move
+    (DESIGN.md §4): depth passes 16 B/Gaussian (first one 12: the ids are generated), tile passes
+    16 B/pair, the last one 8 + 4 (depth gather) read + 12 written."""
     per_vis = (44 + 12 + 48) if precomp else 284
+    passes = depth_passes + tile_passes
     return {
-        "preprocess": per_vis * P_visible + 20 * P_culled,
+        "preprocess": per_vis * P_visible + 20 * P_culled + 4 * P,   # + the 4-byte depth key
         "scan": 0,
-        "duplicate": 20 * P_visible + 12 * R,
-        "sort": (8 + passes * 24) * R,
-        "sort_pass": 24 * R,
+        "duplicate": 20 * P_visible + 8 * R,                         # 32-bit tile key + id per pair
+        "sort_survey": (8 + passes * 24) * R,                        # §8(d): 64-bit keys, every pass over R pairs
+        "sort_moved": 4 * P + (16 * depth_passes - 4) * P + (16 * (tile_passes - 1) + 24) * R,
+        "depth_pass": 16 * P,
+        "tile_pass": 16 * R,
+        "tile_pass_last": 24 * R,
         "ranges": 8 * R + 8 * tiles,
     }
 
@@ -313,9 +319,11 @@ def main():
             if i >= 2:
                 stage_runs.append(tm)
         keys = ("preprocess_ms", "scan_ms", "duplicate_ms", "sort_ms", "ranges_ms", "blend_ms", "total_ms",
-                "sort_hist_ms")
+                "sort_hist_ms", "depth_sort_ms")
         st = {k: statistics.mean(r[k] for r in stage_runs) for k in keys}
         passes = stage_runs[0]["sort_passes"]
+        dpasses = stage_runs[0]["depth_passes"]
+        tpasses = passes - dpasses
         pass_ms = [statistics.mean(r["sort_pass_ms"][i] for r in stage_runs) for i in range(passes)]
         R = stage_runs[0]["num_rendered"]
         launches_per_frame = stage_runs[0]["kernel_launches"]
@@ -331,7 +339,7 @@ def main():
         del g
         torch.cuda.empty_cache()
         tiles = ((W + 15) // 16) * ((H + 15) // 16)
-        ab = algorithmic_bytes(P_vis, sc.P - P_vis, R, tiles, passes, sc.colors_precomp is not None)
+        ab = algorithmic_bytes(sc.P, P_vis, sc.P - P_vis, R, tiles, dpasses, tpasses, sc.colors_precomp is not None)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -347,8 +355,14 @@ def main():
             "preprocess": {"ms": st["preprocess_ms"], "GB/s": gbs(ab["preprocess"], st["preprocess_ms"])},
             "scan": {"ms": st["scan_ms"]},
             "duplicate": {"ms": st["duplicate_ms"], "GB/s": gbs(ab["duplicate"], st["duplicate_ms"])},
-            "sort": {"ms": st["sort_ms"], "GB/s": gbs(ab["sort"], st["sort_ms"]), "hist_ms": st["sort_hist_ms"],
-                     "pass_ms": pass_ms, "passes": passes},
+            # the LSD sort = depth half (P Gaussians, before duplication) + tile half (R pairs).  "GB/s" rates the
+            # whole sort by SURVEY §8(d)'s 152 B/pair (what a 6-pass sort of R pairs moves); "GB/s_moved" by the
+            # bytes the split design is defined to move.
+            "sort": {"ms": st["sort_ms"] + st["depth_sort_ms"], "depth_ms": st["depth_sort_ms"],
+                     "tile_ms": st["sort_ms"],
+                     "GB/s": gbs(ab["sort_survey"], st["sort_ms"] + st["depth_sort_ms"]),
+                     "GB/s_moved": gbs(ab["sort_moved"], st["sort_ms"] + st["depth_sort_ms"]),
+                     "hist_ms": st["sort_hist_ms"], "pass_ms": pass_ms, "passes": passes, "depth_passes": dpasses},
             "ranges": {"ms": st["ranges_ms"], "GB/s": gbs(ab["ranges"], st["ranges_ms"])},
             "blend": {"ms": st["blend_ms"]},
             "frame_serial_ms": st["total_ms"],
@@ -356,16 +370,18 @@ def main():
         for v in stages.values():
             if isinstance(v, dict) and v.get("GB/s"):
                 v["frac_of_peak"] = v["GB/s"] / peak
-        pre_sort_b = ab["preprocess"] + ab["duplicate"] + ab["sort"] + ab["ranges"]
-        pre_sort_ms = st["preprocess_ms"] + st["scan_ms"] + st["duplicate_ms"] + st["sort_ms"] + st["ranges_ms"]
+        pre_sort_b = ab["preprocess"] + ab["duplicate"] + ab["sort_survey"] + ab["ranges"]
+        pre_sort_ms = (st["preprocess_ms"] + st["scan_ms"] + st["depth_sort_ms"] + st["duplicate_ms"] + st["sort_ms"] +
+                       st["ranges_ms"])
         stages["preprocess_plus_sort"] = {"ms": pre_sort_ms, "GB/s": gbs(pre_sort_b, pre_sort_ms),
                                           "frac_of_peak": gbs(pre_sort_b, pre_sort_ms) / peak}
-        # dominant HBM kernel: a single launch — preprocess, or the mean onesweep pass
+        # dominant HBM kernel: a single launch — preprocess, duplication, or a tile-digit onesweep pass
+        tile_ms = pass_ms[dpasses:]
+        osw = "onesweep_kernel<u32> (mean of %d tile-digit passes over R pairs)" % tpasses
         cand = {"preprocess_kernel": (ab["preprocess"], st["preprocess_ms"]),
-                "onesweep_kernel (mean of %d digit passes)" % passes: (ab["sort_pass"], statistics.mean(pass_ms)),
-                "duplicate_kernel": (ab["duplicate"], st["duplicate_ms"])}
-        share = {"preprocess_kernel": st["preprocess_ms"], "duplicate_kernel": st["duplicate_ms"]}
-        share["onesweep_kernel (mean of %d digit passes)" % passes] = sum(pass_ms)
+                osw: ((ab["tile_pass"] * (tpasses - 1) + ab["tile_pass_last"]) / max(tpasses, 1), statistics.mean(tile_ms)),
+                "duplicate_sorted_kernel": (ab["duplicate"], st["duplicate_ms"])}
+        share = {"preprocess_kernel": st["preprocess_ms"], "duplicate_sorted_kernel": st["duplicate_ms"], osw: sum(tile_ms)}
         dom = max(share, key=share.get)
         roof = {"bound": "hbm", "kernel": dom, "achieved": gbs(*cand[dom]), "peak": peak, "unit": "GB/s",
                 "frac": gbs(*cand[dom]) / peak, "traffic": None, "peak_source": peak_src,

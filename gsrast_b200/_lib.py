@@ -26,7 +26,8 @@ class StageTimes(C.Structure):
     _fields_ = [(n, C.c_float) for n in
                 ("preprocess_ms", "scan_ms", "duplicate_ms", "sort_ms", "ranges_ms", "blend_ms", "total_ms")] + \
                [("num_rendered", C.c_int), ("sort_passes", C.c_int), ("kernel_launches", C.c_int),
-                ("sort_hist_ms", C.c_float), ("sort_pass_ms", C.c_float * 8)]
+                ("sort_hist_ms", C.c_float), ("sort_pass_ms", C.c_float * 8),
+                ("depth_sort_ms", C.c_float), ("depth_passes", C.c_int)]
 
     def as_dict(self):
         d = {n: getattr(self, n) for n, _ in self._fields_}
@@ -69,7 +70,10 @@ class ForwardArgs(C.Structure):
 class GeometryState(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("depths", "clamped", "internal_radii", "means2D", "cov3D", "conic_opacity", "rgb", "tiles_touched",
-                 "point_offsets", "block_sums")] + [("scan_size", C.c_size_t)]
+                 "point_offsets", "block_sums")] + [("scan_size", C.c_size_t)] + \
+               [("depth_keys", C.c_void_p), ("tile_rects", C.c_void_p), ("depth_sort_keys", C.c_void_p * 2), ("depth_sort_ids", C.c_void_p * 2),
+                ("depth_sort_space", C.c_void_p), ("depth_sort_size", C.c_size_t),
+                ("dup_scan_state", C.c_void_p), ("dup_scan_size", C.c_size_t)]
 
 
 class ImageState(C.Structure):

@@ -5,12 +5,11 @@
 //   duplicateWithKeys                                          GSCuda.cu:422-475 (launch :787)
 //   cudaMemset(ranges) + identifyTileRanges                    GSCuda.cu:800-801, 504-538
 //
-// The scan is split in three: per-block sums (written by preprocess), a single-CTA scan of
-// those sums (scan_block_sums_kernel, which also publishes num_rendered straight into mapped
-// pinned host memory), and the intra-block scan, which is fused into the duplication kernel.
-// Duplication is load-balanced: the 256 Gaussians of a block pool their tile counts and the
-// block's threads walk the pooled output range item by item, so one huge splat does not
-// serialise a thread and the key/value stores are fully coalesced.
+// num_rendered comes from per-block sums (written by preprocess) and a single-CTA scan of those
+// sums (scan_block_sums_kernel, which publishes the total straight into mapped pinned host memory).
+// Duplication runs on the Gaussians in DEPTH order (they are radix-sorted by their depth key while
+// the host waits for num_rendered, see radix_sort.cu) with its own chained scan, is load-balanced
+// (the 256 Gaussians of a block pool their tile counts) and emits 32-bit tile keys.
 #include "gsr_common.cuh"
 
 namespace gsr {
@@ -67,34 +66,31 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(uint32_t*
     }
 }
 
-__device__ __forceinline__ void get_rect_dev(float px, float py, int ex, int ey, int gx, int gy, int& minx, int& miny,
-                                             int& maxx, int& maxy) {
-    // x / 16.0f == x * 0.0625f bit for bit (exact power-of-two scaling)
-    minx = min(gx, max(0, __float2int_rz(fmul(fsub(px, (float)ex), 1.0f / TILE_X))));
-    miny = min(gy, max(0, __float2int_rz(fmul(fsub(py, (float)ey), 1.0f / TILE_Y))));
-    maxx = min(gx, max(0, __float2int_rz(fmul(fsub(fadd(fadd(px, (float)ex), (float)TILE_X), 1.0f), 1.0f / TILE_X))));
-    maxy = min(gy, max(0, __float2int_rz(fmul(fsub(fadd(fadd(py, (float)ey), (float)TILE_Y), 1.0f), 1.0f / TILE_Y))));
+// Status words of the chained scan carry flag and count in ONE 32-bit word (2 flag bits + 30-bit
+// count; num_rendered < 2^30 is enforced by the caller), so relaxed gpu-scope accesses suffice.
+constexpr uint32_t SCAN_AGG = 1u << 30;
+constexpr uint32_t SCAN_INC = 2u << 30;
+constexpr uint32_t SCAN_FLAGS = 3u << 30;
+
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// One block = the same 256 Gaussians as in preprocess.
-__global__ void __launch_bounds__(PRE_THREADS) duplicate_kernel(
-    const int P, const int grid_x, const int grid_y, const float2* __restrict__ means2D,
-    const float* __restrict__ depths, const uint32_t* __restrict__ tiles_touched,
-    const uint32_t* __restrict__ block_offsets, const int* __restrict__ radii, const int2* __restrict__ rects,
-    uint32_t* __restrict__ point_offsets, uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
-    __shared__ uint32_t s_excl[PRE_THREADS + 1];
+// Inclusive scan of tiles_touched in index order — the array cub::DeviceScan::InclusiveSum leaves in
+// pointOffsets (GSCuda.cu:771), which the Inspector reads (Inspector.cpp:174-188).  The pipeline itself
+// consumes the scan in depth order (duplicate_sorted_kernel), so this is materialised on the side.
+__global__ void __launch_bounds__(PRE_THREADS) point_offsets_kernel(const int P, const uint32_t* __restrict__ tiles_touched,
+                                                                    const uint32_t* __restrict__ block_offsets,
+                                                                    uint32_t* __restrict__ point_offsets) {
     __shared__ uint32_t s_warp[PRE_THREADS / 32];
-    __shared__ uint32_t s_depth[PRE_THREADS];
-    __shared__ uint32_t s_origin[PRE_THREADS];  // miny << 16 | minx
-    __shared__ uint32_t s_width[PRE_THREADS];
-
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int base = blockIdx.x * PRE_THREADS;
-    const int idx = base + tid;
-    const bool valid = idx < P;
-
-    // Culled Gaussians have tiles_touched == 0 (radii <= 0), so they drop out naturally.
-    const uint32_t cnt = valid ? tiles_touched[idx] : 0u;
+    const int idx = blockIdx.x * PRE_THREADS + tid;
+    const uint32_t cnt = idx < P ? tiles_touched[idx] : 0u;
     uint32_t incl = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -107,50 +103,131 @@ __global__ void __launch_bounds__(PRE_THREADS) duplicate_kernel(
 #pragma unroll
     for (int w = 0; w < PRE_THREADS / 32; ++w)
         if (w < warp) woff += s_warp[w];
+    if (idx < P) point_offsets[idx] = block_offsets[blockIdx.x] + woff + incl;
+}
+
+// Duplication in depth order.  Block b (handed out by ticket, so predecessors have always started)
+// takes the 256 Gaussians sorted_ids[256b .. 256b+255], scans their tile counts, obtains its global
+// offset by a chained scan with decoupled look-back (warp 0 inspects 32 predecessors per step), and
+// emits every (tile, Gaussian) pair: rows outer, columns inner (GSCuda.cu:461-474).  The work is
+// pooled: the block's threads walk the pooled output range item by item, so one huge splat does not
+// serialise a thread and the stores are fully coalesced.  The digit histograms of the tile passes are
+// counted here (shared-memory atomics, flushed once per block), so the sort never re-reads the keys.
+__global__ void __launch_bounds__(PRE_THREADS) duplicate_sorted_kernel(
+    const int P, const int grid_x, const uint32_t* __restrict__ sorted_ids, const uint2* __restrict__ tile_rects,
+    uint32_t* __restrict__ scan_state, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+    uint32_t* __restrict__ hist, const int tile_bits) {
+    __shared__ uint32_t s_excl[PRE_THREADS + 1];
+    __shared__ uint32_t s_warp[PRE_THREADS / 32];
+    __shared__ uint32_t s_gid[PRE_THREADS];
+    __shared__ uint32_t s_origin[PRE_THREADS];  // miny << 16 | minx
+    __shared__ uint32_t s_width[PRE_THREADS];
+    __shared__ uint32_t s_hist[4 * 256];
+    __shared__ uint32_t s_ctl[2];  // block ticket, global offset
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int passes = (tile_bits + 7) >> 3;
+    if (tid == 0) s_ctl[0] = atomicAdd(scan_state, 1u);
+    for (int i = tid; i < passes * 256; i += PRE_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    const uint32_t b = s_ctl[0];
+    uint32_t* status = scan_state + 2;
+    const int i = (int)b * PRE_THREADS + tid;
+    const bool valid = i < P;
+
+    // One 8-byte gather per Gaussian: the tile rect preprocess computed with getRect (GSCuda.cu:237-259;
+    // duplicateWithKeys recomputes the same rect, :445-458).  Gaussians that emit nothing (radii <= 0,
+    // GSCuda.cu:440-443) carry an empty rect and sort to the end (key 0xffffffff).
+    const uint32_t g = valid ? __ldg(sorted_ids + i) : 0u;
+    const uint2 rec = valid ? __ldg(tile_rects + g) : make_uint2(0u, 0u);
+    const uint32_t cnt = (rec.y >> 16) * (rec.y & 0xffffu);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < PRE_THREADS / 32; ++w) {
+        if (w < warp) woff += s_warp[w];
+        total += s_warp[w];
+    }
     incl += woff;
-    const uint32_t boff = block_offsets[blockIdx.x];
-    if (valid) point_offsets[idx] = boff + incl;  // inclusive scan, as GSCuda.cu:771 produces
     s_excl[tid] = incl - cnt;
     if (tid == PRE_THREADS - 1) s_excl[PRE_THREADS] = incl;
 
-    if (cnt > 0) {
-        const float2 m = means2D[idx];
-        int minx, miny, maxx, maxy;
-        if (rects == nullptr) {
-            const int r = radii[idx];
-            get_rect_dev(m.x, m.y, r, r, grid_x, grid_y, minx, miny, maxx, maxy);
-        } else {
-            const int2 e = rects[idx];
-            get_rect_dev(m.x, m.y, e.x, e.y, grid_x, grid_y, minx, miny, maxx, maxy);
+    // ---- chained scan across blocks ---------------------------------------------------------
+    if (warp == 0) {
+        if (lane == 0) st_relaxed_u32(status + b, (b == 0 ? SCAN_INC : SCAN_AGG) | total);
+        uint32_t excl = 0;
+        if (b > 0) {
+            int64_t t = (int64_t)b - 1;
+            uint32_t spins = 0;
+            while (true) {
+                const int64_t idx = t - lane;
+                uint32_t v = SCAN_INC;  // before the first block: inclusive prefix 0
+                if (idx >= 0) {
+                    v = ld_relaxed_u32(status + idx);
+                    while ((v & SCAN_FLAGS) == 0) {
+                        if (++spins > (1u << 22)) {  // watchdog: never expected to trip
+                            atomicExch(scan_state + 1, 1u);
+                            v = SCAN_INC;
+                            break;
+                        }
+                        __nanosleep(20);
+                        v = ld_relaxed_u32(status + idx);
+                    }
+                }
+                const unsigned inc = __ballot_sync(0xffffffffu, (v & SCAN_FLAGS) == SCAN_INC);
+                const int first = inc ? (__ffs(inc) - 1) : 32;
+                excl += __reduce_add_sync(0xffffffffu, (lane <= first) ? (v & ~SCAN_FLAGS) : 0u);
+                if (inc) break;
+                t -= 32;
+            }
+            if (lane == 0) st_relaxed_u32(status + b, SCAN_INC | (excl + total));
         }
-        s_depth[tid] = __float_as_uint(depths[idx]);
-        s_origin[tid] = ((uint32_t)miny << 16) | (uint32_t)minx;
-        // GSCuda.cu:440-443: Gaussians with radii <= 0 emit nothing (their slots stay unwritten)
-        s_width[tid] = (radii[idx] > 0) ? (uint32_t)(maxx - minx) : 0u;
+        if (lane == 0) s_ctl[1] = excl;
+    }
+
+    if (cnt > 0) {
+        s_gid[tid] = g;
+        s_origin[tid] = rec.x;
+        s_width[tid] = rec.y & 0xffffu;
     }
     __syncthreads();
 
-    const uint32_t total = s_excl[PRE_THREADS];
+    const uint32_t boff = s_ctl[1];
     for (uint32_t k = tid; k < total; k += PRE_THREADS) {
-        // largest g with s_excl[g] <= k
+        // largest j with s_excl[j] <= k
         int lo = 0, hi = PRE_THREADS - 1;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
             const int mid = (lo + hi + 1) >> 1;
             if (s_excl[mid] <= k) lo = mid; else hi = mid - 1;
         }
-        const int g = lo;
-        const uint32_t t = k - s_excl[g];
-        const uint32_t w = s_width[g];
-        if (w == 0) continue;
+        const uint32_t t = k - s_excl[lo];
+        const uint32_t w = s_width[lo];
         const uint32_t ty = t / w, tx = t - ty * w;
-        const uint32_t org = s_origin[g];
-        const uint32_t y = (org >> 16) + ty, x = (org & 0xffffu) + tx;
-        // key = tile id << 32 | depth bits  (GSCuda.cu:466-471); rows outer, columns inner
-        const uint64_t key = ((uint64_t)(y * (uint32_t)grid_x + x) << 32) | (uint64_t)s_depth[g];
+        const uint32_t org = s_origin[lo];
+        // key = tile id (GSCuda.cu:466-471: the depth half is re-attached by the last sort pass)
+        const uint32_t tile = ((org >> 16) + ty) * (uint32_t)grid_x + (org & 0xffffu) + tx;
         const size_t o = (size_t)boff + k;
-        keys_out[o] = key;
-        vals_out[o] = (uint32_t)(base + g);
+        keys_out[o] = tile;
+        vals_out[o] = s_gid[lo];
+        for (int ps = 0; ps < passes; ++ps) {
+            const int nb = min(8, tile_bits - 8 * ps);
+            atomicAdd(&s_hist[ps * 256 + ((tile >> (8 * ps)) & ((1u << nb) - 1u))], 1u);
+        }
+    }
+    __syncthreads();
+    if (total > 0) {
+        for (int j = tid; j < passes * 256; j += PRE_THREADS) {
+            const uint32_t c = s_hist[j];
+            if (c) atomicAdd(hist + j, c);
+        }
     }
 }
 
@@ -199,15 +276,29 @@ int launch_scan_block_sums(uint32_t* block_sums, int num_blocks, uint32_t* total
     return e == cudaSuccess ? 1 : -(int)e;
 }
 
-int launch_duplicate(int P, int grid_x, int grid_y, const float* means2D, const float* depths,
-                     const uint32_t* tiles_touched, const uint32_t* block_sums, const int* radii, const int* rects,
-                     uint32_t* point_offsets, uint64_t* keys_out, uint32_t* vals_out, cudaStream_t s) {
+int launch_point_offsets(int P, const uint32_t* tiles_touched, const uint32_t* block_sums, uint32_t* point_offsets,
+                         cudaStream_t s) {
     if (P <= 0) return 0;
     const int blocks = (P + PRE_THREADS - 1) / PRE_THREADS;
-    duplicate_kernel<<<blocks, PRE_THREADS, 0, s>>>(P, grid_x, grid_y, reinterpret_cast<const float2*>(means2D), depths,
-                                                    tiles_touched, block_sums, radii,
-                                                    reinterpret_cast<const int2*>(rects), point_offsets, keys_out,
-                                                    vals_out);
+    point_offsets_kernel<<<blocks, PRE_THREADS, 0, s>>>(P, tiles_touched, block_sums, point_offsets);
+    cudaError_t e = cudaPeekAtLastError();
+    return e == cudaSuccess ? 1 : -(int)e;
+}
+
+size_t dup_scan_state_bytes(int P) {
+    const size_t blocks = (size_t)((P > 0 ? P : 0) + PRE_THREADS - 1) / PRE_THREADS;
+    return (blocks + 2 + 30) / 32 * 32 * sizeof(uint32_t);
+}
+
+int launch_duplicate_sorted(int P, int grid_x, const uint32_t* sorted_ids, const uint32_t* tile_rects,
+                            uint32_t* scan_state, uint32_t* keys32_out, uint32_t* vals_out, uint32_t* hist,
+                            int tile_bits, cudaStream_t s) {
+    if (P <= 0) return 0;
+    if (tile_bits < 1 || tile_bits > 32) return GSR_ERR_INVALID_ARG;
+    const int blocks = (P + PRE_THREADS - 1) / PRE_THREADS;
+    duplicate_sorted_kernel<<<blocks, PRE_THREADS, 0, s>>>(P, grid_x, sorted_ids,
+                                                           reinterpret_cast<const uint2*>(tile_rects), scan_state,
+                                                           keys32_out, vals_out, hist, tile_bits);
     cudaError_t e = cudaPeekAtLastError();
     return e == cudaSuccess ? 1 : -(int)e;
 }

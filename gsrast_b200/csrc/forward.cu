@@ -8,6 +8,12 @@
 //   * the only host<->device round trip is the 4-byte num_rendered, written by the scan
 //     kernel straight into mapped pinned memory (the reference does a blocking cudaMemcpy,
 //     GSCuda.cu:772, and its caller a cudaDeviceSynchronize per call, CudaBuffer.hpp:8-12);
+//     the host waits on an event recorded right behind that kernel, and the GPU spends the
+//     wait on the depth half of the radix sort, which needs neither num_rendered nor the
+//     binning chunk;
+//   * the LSD radix sort is split: depth digits are sorted per Gaussian (P records) before
+//     duplication, only the tile digits per pair (radix_sort.cu explains why this is the
+//     same sort);
 //   * `ranges` is one entry per tile, not per pixel (GSCuda.cu:800 clears W*H entries);
 //   * everything runs on the caller's stream.
 #include <algorithm>
@@ -49,13 +55,18 @@ int ensure_slot(HostSlot& s) {
     void* d = nullptr;
     GSR_CUDA_TRY(cudaHostGetDevicePointer(&d, h, 0));
     s.dev = static_cast<uint32_t*>(d);
+    if (s.landed) cudaEventDestroy(s.landed);
+    s.landed = nullptr;
+    GSR_CUDA_TRY(cudaEventCreateWithFlags(&s.landed, cudaEventDisableTiming));
     s.device = dev;
     return 0;
 }
 
 void release_slot(HostSlot& s) {
     if (s.host) cudaFreeHost(s.host);
+    if (s.landed) cudaEventDestroy(s.landed);
     s.host = s.dev = nullptr;
+    s.landed = nullptr;
     s.device = -1;
 }
 
@@ -64,7 +75,7 @@ namespace {
 struct StageTimer {
     bool on = false;
     cudaStream_t s = nullptr;
-    cudaEvent_t ev[8];
+    cudaEvent_t ev[10];
     int n = 0;
     int init(bool enable, cudaStream_t stream) {
         on = enable;
@@ -74,7 +85,7 @@ struct StageTimer {
         return 0;
     }
     void mark() {
-        if (on && n < 8) cudaEventRecord(ev[n++], s);
+        if (on && n < 10) cudaEventRecord(ev[n++], s);
     }
     float ms(int a, int b) {
         float t = 0.f;
@@ -124,6 +135,14 @@ size_t gsr_geometry_state_map(char* chunk, int P, gsr_geometry_state* g) {
     st.scan_size = ((size_t)num_pre_blocks(P) + 4) * sizeof(uint32_t);
     obtain(c, st.block_sums, st.scan_size);
     obtain(c, st.point_offsets, n * sizeof(uint32_t));
+    obtain(c, st.depth_keys, n * sizeof(uint32_t));
+    obtain(c, st.tile_rects, n * 2 * sizeof(uint32_t));
+    for (int i = 0; i < 2; ++i) obtain(c, st.depth_sort_keys[i], n * sizeof(uint32_t));
+    for (int i = 0; i < 2; ++i) obtain(c, st.depth_sort_ids[i], n * sizeof(uint32_t));
+    st.depth_sort_size = sort_temp_bytes(n);
+    obtain(c, st.depth_sort_space, st.depth_sort_size);
+    st.dup_scan_size = dup_scan_state_bytes(P);
+    obtain(c, st.dup_scan_state, st.dup_scan_size);
     if (g) *g = st;
     return (size_t)(c - chunk);
 }
@@ -148,7 +167,7 @@ size_t gsr_binning_state_map(char* chunk, size_t R, gsr_binning_state* b) {
     obtain(c, st.point_list_keys, R * sizeof(uint64_t));
     obtain(c, st.point_list_unsorted, R * sizeof(uint32_t));
     obtain(c, st.point_list, R * sizeof(uint32_t));
-    st.sorting_size = sort_temp_bytes(R);
+    st.sorting_size = (R * sizeof(uint32_t) + 127) / 128 * 128 + sort_temp_bytes(R);
     obtain(c, st.list_sorting_space, st.sorting_size);
     if (b) *b = st;
     return (size_t)(c - chunk);
@@ -208,10 +227,32 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
     gsr_image_state img;
     gsr_image_state_map(ichunk, W, H, &img);
 
+    const int tile_bits = (int)gsr_get_higher_msb((uint32_t)tiles);  // GSCuda.cu:791-797: end_bit = 32 + this
+    const int tile_passes = sort_num_passes(tile_bits);
+    const int depth_passes = sort_num_passes(32);
+    cudaEvent_t sort_ev[12];
+    const bool sort_timed = tm.on;
+    if (sort_timed)
+        for (auto& e : sort_ev) cudaEventCreate(&e);
+#define GSR_FAIL(code)                                     \
+    do {                                                   \
+        if (sort_timed)                                    \
+            for (auto& e : sort_ev) cudaEventDestroy(e);   \
+        tm.destroy();                                      \
+        return (code);                                     \
+    } while (0)
+#undef GSR_STAGE
+#define GSR_STAGE(call)          \
+    do {                         \
+        rc = (call);             \
+        if (rc < 0) GSR_FAIL(rc);\
+        launches += rc;          \
+    } while (0)
+
     uint32_t R = 0;
     tm.mark();  // 0
     if (P > 0) {
-        if ((rc = ensure_slot(slot)) < 0) { tm.destroy(); return rc; }
+        if ((rc = ensure_slot(slot)) < 0) GSR_FAIL(rc);
         PreprocessParams pp;
         memset(&pp, 0, sizeof(pp));
         pp.P = P; pp.D = a->D; pp.M = a->M; pp.W = W; pp.H = H; pp.grid_x = gx; pp.grid_y = gy;
@@ -233,16 +274,35 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         pp.radii = radii; pp.rects = a->rects; pp.depths = geom.depths; pp.clamped = geom.clamped;
         pp.means2D = geom.means2D; pp.cov3D = geom.cov3D; pp.conic_opacity = geom.conic_opacity;
         pp.rgb = geom.rgb; pp.tiles_touched = geom.tiles_touched; pp.block_sums = geom.block_sums;
+        pp.depth_keys = geom.depth_keys; pp.tile_rects = geom.tile_rects;
         GSR_STAGE(launch_preprocess(pp, compat, s));
         tm.mark();  // 1
         const int nb = num_pre_blocks(P);
         GSR_STAGE(launch_scan_block_sums(geom.block_sums, nb, geom.block_sums + nb, slot.dev, s));
+        cudaError_t e = cudaEventRecord(slot.landed, s);
+        if (e != cudaSuccess) GSR_FAIL(-(int)e);
         tm.mark();  // 2
+        // ---- depth half of the sort: P records, queued before the host waits --------------------
+        if (!sort32_prepare(geom.depth_sort_space, (size_t)P, 32, s)) GSR_FAIL(-(int)cudaGetLastError());
+        Sort32Plan dp;
+        memset(&dp, 0, sizeof(dp));
+        dp.n = (size_t)P; dp.end_bit = 32;
+        dp.keys_in = geom.depth_keys; dp.vals_in = nullptr;
+        dp.kbuf[0] = geom.depth_sort_keys[0]; dp.kbuf[1] = geom.depth_sort_keys[1];
+        dp.vbuf[0] = geom.depth_sort_ids[0]; dp.vbuf[1] = geom.depth_sort_ids[1];
+        dp.keys_out = geom.depth_sort_keys[1]; dp.vals_out = geom.depth_sort_ids[1];
+        dp.temp = geom.depth_sort_space; dp.hist_ready = false;
+        GSR_STAGE(launch_sort32(dp, s, sort_timed ? sort_ev : nullptr));
+        GSR_STAGE(launch_point_offsets(P, geom.tiles_touched, geom.block_sums, geom.point_offsets, s));
+        e = cudaMemsetAsync(geom.dup_scan_state, 0, geom.dup_scan_size, s);
+        if (e != cudaSuccess) GSR_FAIL(-(int)e);
+        tm.mark();  // 3
         // the one host round trip: num_rendered decides the binning allocation (GSCuda.cu:772,782)
-        cudaError_t e = cudaStreamSynchronize(s);
-        if (e != cudaSuccess) { tm.destroy(); return -(int)e; }
+        e = cudaEventSynchronize(slot.landed);
+        if (e != cudaSuccess) GSR_FAIL(-(int)e);
         R = *static_cast<volatile uint32_t*>(slot.host);
     } else {
+        tm.mark();
         tm.mark();
         tm.mark();
     }
@@ -255,48 +315,46 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
             memset(a->timings, 0, sizeof(*a->timings));
             a->timings->preprocess_ms = tm.ms(0, 1);
             a->timings->scan_ms = tm.ms(1, 2);
-            a->timings->total_ms = tm.ms(0, 2);
+            a->timings->depth_sort_ms = tm.ms(2, 3);
+            a->timings->total_ms = tm.ms(0, 3);
             a->timings->kernel_launches = launches;
         }
-        tm.destroy();
-        return 0;
+        GSR_FAIL(0);
     }
-    if (R >= (1u << 30)) { tm.destroy(); return GSR_ERR_TOO_MANY_PAIRS; }
+    if (R >= (1u << 30)) GSR_FAIL(GSR_ERR_TOO_MANY_PAIRS);
 
     // binning chunk (GSCuda.cu:782-784)
     char* bchunk = a->binning_alloc(gsr_binning_state_required(R), a->binning_user);
-    if (!bchunk) { tm.destroy(); return GSR_ERR_ALLOC_FAILED; }
+    if (!bchunk) GSR_FAIL(GSR_ERR_ALLOC_FAILED);
     gsr_binning_state bin;
     gsr_binning_state_map(bchunk, R, &bin);
 
-    const int end_bit = 32 + (int)gsr_get_higher_msb((uint32_t)tiles);  // GSCuda.cu:791-797
-    const int passes = sort_num_passes(end_bit);
-    // Ping-pong start buffer chosen so the sorted lists land in point_list_keys / point_list.
-    const bool start_in_sorted = (passes % 2) == 0;
-    uint64_t* ka = start_in_sorted ? bin.point_list_keys : bin.point_list_keys_unsorted;
-    uint32_t* va = start_in_sorted ? bin.point_list : bin.point_list_unsorted;
-    uint64_t* kb = start_in_sorted ? bin.point_list_keys_unsorted : bin.point_list_keys;
-    uint32_t* vb = start_in_sorted ? bin.point_list_unsorted : bin.point_list;
-
-    GSR_STAGE(launch_duplicate(P, gx, gy, geom.means2D, geom.depths, geom.tiles_touched, geom.block_sums, radii,
-                               a->rects, geom.point_offsets, ka, va, s));
-    tm.mark();  // 3
-    bool in_a = false;
-    cudaEvent_t sort_ev[10];
-    const bool sort_timed = tm.on;
-    if (sort_timed)
-        for (auto& e : sort_ev) cudaEventCreate(&e);
-    rc = launch_sort_pairs(ka, va, kb, vb, R, end_bit, bin.list_sorting_space, &in_a, s, sort_timed ? sort_ev : nullptr);
-    if (rc < 0) {
-        if (sort_timed)
-            for (auto& e : sort_ev) cudaEventDestroy(e);
-        tm.destroy();
-        return rc;
-    }
-    launches += rc;
+    // ---- duplication in depth order + tile half of the sort ----------------------------------
+    uint32_t* k32[2] = {reinterpret_cast<uint32_t*>(bin.point_list_keys_unsorted),
+                        reinterpret_cast<uint32_t*>(bin.point_list_keys_unsorted) + R};
+    uint32_t* v32[2] = {bin.point_list_unsorted, reinterpret_cast<uint32_t*>(bin.list_sorting_space)};
+    char* tile_temp = bin.list_sorting_space + ((size_t)R * sizeof(uint32_t) + 127) / 128 * 128;
+    uint32_t* tile_hist = sort32_prepare(tile_temp, (size_t)R, tile_bits, s);
+    if (!tile_hist) GSR_FAIL(-(int)cudaGetLastError());
+    GSR_STAGE(launch_duplicate_sorted(P, gx, geom.depth_sort_ids[1], geom.tile_rects, geom.dup_scan_state, k32[0],
+                                      v32[0], tile_hist, tile_bits, s));
     tm.mark();  // 4
-    GSR_STAGE(launch_identify_ranges(bin.point_list_keys, R, img.ranges, tiles, compat, s));
+    {
+        Sort32Plan tp;
+        memset(&tp, 0, sizeof(tp));
+        tp.n = (size_t)R; tp.end_bit = tile_bits;
+        tp.keys_in = k32[0]; tp.vals_in = v32[0];
+        tp.kbuf[0] = k32[1]; tp.kbuf[1] = k32[0];
+        tp.vbuf[0] = v32[1]; tp.vbuf[1] = v32[0];
+        tp.keys_out = nullptr; tp.vals_out = bin.point_list;
+        tp.expand_low = reinterpret_cast<const uint32_t*>(geom.depths);  // key = tile << 32 | depth bits
+        tp.keys_out64 = bin.point_list_keys;
+        tp.temp = tile_temp; tp.hist_ready = true;
+        GSR_STAGE(launch_sort32(tp, s, sort_timed ? sort_ev + 6 : nullptr));
+    }
     tm.mark();  // 5
+    GSR_STAGE(launch_identify_ranges(bin.point_list_keys, R, img.ranges, tiles, compat, s));
+    tm.mark();  // 6
 
     BlendParams bp;
     memset(&bp, 0, sizeof(bp));
@@ -308,31 +366,39 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
     bp.t_min = compat ? 0.001f : 0.0001f;  // GSCuda.cu:653 vs contract
     bp.tile_order = nullptr;
     GSR_STAGE(launch_blend(bp, (a->flags & GSR_FLAG_BLEND_SIMPLE) != 0, s));
-    tm.mark();  // 6
+    tm.mark();  // 7
 #undef GSR_STAGE
 
     if (a->timings) {
         cudaError_t e = cudaStreamSynchronize(s);
-        if (e != cudaSuccess) { tm.destroy(); return -(int)e; }
+        if (e != cudaSuccess) GSR_FAIL(-(int)e);
         gsr_stage_times* t = a->timings;
+        memset(t, 0, sizeof(*t));
         t->preprocess_ms = tm.ms(0, 1);
         t->scan_ms = tm.ms(1, 2);
-        t->duplicate_ms = tm.ms(2, 3);
-        t->sort_ms = tm.ms(3, 4);
-        t->ranges_ms = tm.ms(4, 5);
-        t->blend_ms = tm.ms(5, 6);
-        t->total_ms = tm.ms(0, 6);
+        t->depth_sort_ms = tm.ms(2, 3);
+        t->duplicate_ms = tm.ms(3, 4);
+        t->sort_ms = tm.ms(4, 5);
+        t->ranges_ms = tm.ms(5, 6);
+        t->blend_ms = tm.ms(6, 7);
+        t->total_ms = tm.ms(0, 7);
         t->num_rendered = (int)R;
-        t->sort_passes = passes;
+        t->depth_passes = depth_passes;
+        t->sort_passes = depth_passes + tile_passes;
         t->kernel_launches = launches;
-        t->sort_hist_ms = 0.f;
-        for (int i = 0; i < 8; ++i) t->sort_pass_ms[i] = 0.f;
-        cudaEventElapsedTime(&t->sort_hist_ms, sort_ev[0], sort_ev[1]);
-        for (int i = 0; i < passes && i < 8; ++i) cudaEventElapsedTime(&t->sort_pass_ms[i], sort_ev[1 + i], sort_ev[2 + i]);
+        float h0 = 0.f, h1 = 0.f;
+        cudaEventElapsedTime(&h0, sort_ev[0], sort_ev[1]);
+        cudaEventElapsedTime(&h1, sort_ev[6], sort_ev[7]);
+        t->sort_hist_ms = h0 + h1;
+        for (int i = 0; i < depth_passes && i < 4; ++i) cudaEventElapsedTime(&t->sort_pass_ms[i], sort_ev[1 + i], sort_ev[2 + i]);
+        for (int i = 0; i < tile_passes && depth_passes + i < 8; ++i)
+            cudaEventElapsedTime(&t->sort_pass_ms[depth_passes + i], sort_ev[7 + i], sort_ev[8 + i]);
     }
     if (sort_timed)
         for (auto& e : sort_ev) cudaEventDestroy(e);
     tm.destroy();
+#undef GSR_STAGE
+#undef GSR_FAIL
     return (int)R;
 }
 

@@ -58,15 +58,25 @@ struct PreprocessParams {
     float* rgb;
     uint32_t* tiles_touched;
     uint32_t* block_sums;  // [ceil(P/256)]
+    uint32_t* depth_keys;  // [P] low half of the sort key: depth bits, 0xffffffff when nothing is emitted
+    uint32_t* tile_rects;  // uint2[P]: (miny<<16|minx, height<<16|width) of the tile rect, 0 when nothing is emitted
 };
 
 // stage launchers (each returns the number of kernels it launched, or <0 on error)
 int launch_preprocess(const PreprocessParams& p, bool compat, cudaStream_t s);
 int launch_scan_block_sums(uint32_t* block_sums, int num_blocks, uint32_t* total_dev, uint32_t* total_host_mapped,
                            cudaStream_t s);
-int launch_duplicate(int P, int grid_x, int grid_y, const float* means2D, const float* depths,
-                     const uint32_t* tiles_touched, const uint32_t* block_sums, const int* radii, const int* rects,
-                     uint32_t* point_offsets, uint64_t* keys_out, uint32_t* vals_out, cudaStream_t s);
+// point_offsets[i] = inclusive scan of tiles_touched in index order (GSCuda.cu:771); block_sums must
+// already hold the exclusive block offsets.
+int launch_point_offsets(int P, const uint32_t* tiles_touched, const uint32_t* block_sums, uint32_t* point_offsets,
+                         cudaStream_t s);
+// Emits the (tile, Gaussian) pairs of the Gaussians taken in the order `sorted_ids` (ascending depth
+// key): 32-bit tile keys + Gaussian ids, and accumulates the tile-digit histograms of the following
+// radix passes into `hist` ([passes][256], zeroed).  `scan_state` = num_dup_blocks(P)+2 zeroed words.
+int launch_duplicate_sorted(int P, int grid_x, const uint32_t* sorted_ids, const uint32_t* tile_rects,
+                            uint32_t* scan_state, uint32_t* keys32_out, uint32_t* vals_out, uint32_t* hist,
+                            int tile_bits, cudaStream_t s);
+size_t dup_scan_state_bytes(int P);
 int launch_identify_ranges(const uint64_t* keys, size_t n, uint32_t* ranges, int num_tiles, bool compat,
                            cudaStream_t s);
 
@@ -79,6 +89,30 @@ int sort_num_passes(int end_bit);
 // `events` (optional, passes+2 entries) are recorded before the histogram, after it, and after every pass.
 int launch_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, size_t n, int end_bit,
                       char* temp, bool* result_in_a, cudaStream_t s, cudaEvent_t* events = nullptr);
+
+// 32-bit-key LSD sort over bits [0,end_bit) (<= 4 passes).  Pass p reads the input (p == 0) or
+// buffer (p-1)&1 and writes buffer p&1, the last pass writes the outputs (which may alias a buffer the
+// last pass does not read).  vals_in == nullptr: values are the input positions.  expand_low != nullptr:
+// the last pass writes 64-bit keys (key32 << 32 | expand_low[value]) to keys_out64 instead of keys_out.
+struct Sort32Plan {
+    size_t n;
+    int end_bit;
+    const uint32_t* keys_in;
+    const uint32_t* vals_in;
+    uint32_t* kbuf[2];
+    uint32_t* vbuf[2];
+    uint32_t* keys_out;
+    uint32_t* vals_out;
+    const uint32_t* expand_low;
+    uint64_t* keys_out64;
+    char* temp;       // sort_temp_bytes(n), prepared by sort32_prepare
+    bool hist_ready;  // the producer of keys_in already accumulated the digit histograms
+};
+// Zeroes the histograms / tickets / look-back state in `temp`; returns the histogram array
+// ([pass][256]) for producers that count digits themselves, or nullptr on error.
+uint32_t* sort32_prepare(char* temp, size_t n, int end_bit, cudaStream_t s);
+// `events` (optional, passes+2 entries): before the histogram, after its scan, after every pass.
+int launch_sort32(const Sort32Plan& plan, cudaStream_t s, cudaEvent_t* events = nullptr);
 
 struct BlendParams {
     int W, H, grid_x, grid_y;
@@ -102,6 +136,7 @@ int launch_fill_background(int W, int H, const float* background, float* out_col
 struct HostSlot {
     uint32_t* host = nullptr;
     uint32_t* dev = nullptr;
+    cudaEvent_t landed = nullptr;  // recorded right after the kernel that writes the word
     int device = -1;
 };
 int ensure_slot(HostSlot& s);

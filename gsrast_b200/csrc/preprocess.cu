@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(const Preproces
     const float* pm = s_cam + 16;
 
     uint32_t tiles = 0;
+    uint2 rec = make_uint2(0u, 0u);  // tile rect for the duplication kernel: miny<<16|minx, height<<16|width
     bool need_sh = false;
     float dirx = 0.f, diry = 0.f, dirz = 0.f;
 
@@ -312,6 +313,8 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(const Preproces
             const uint32_t area = (uint32_t)(maxx - minx) * (uint32_t)(maxy - miny);
             if (area != 0) {
                 tiles = area;
+                rec = make_uint2(((uint32_t)miny << 16) | (uint32_t)minx,
+                                 ((uint32_t)(maxy - miny) << 16) | (uint32_t)(maxx - minx));
                 radius_out = ri;
                 p.depths[idx] = depth;
                 reinterpret_cast<float2*>(p.means2D)[idx] = make_float2(ix, iy);
@@ -334,6 +337,9 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(const Preproces
         }
         p.radii[idx] = radius_out;
         p.tiles_touched[idx] = tiles;
+        // low half of the sort key (GSCuda.cu:466-471); Gaussians that emit nothing sort last
+        p.depth_keys[idx] = tiles ? __float_as_uint(depth) : 0xffffffffu;
+        reinterpret_cast<uint2*>(p.tile_rects)[idx] = rec;
     }
 
     // ---- SH colour: 4 lanes per surviving Gaussian -----------------------------------------

@@ -80,10 +80,13 @@ int gsr_forward_gscuda(gsr_alloc_fn geometry_alloc, void* geometry_user, gsr_all
 typedef struct gsr_stage_times {
     float preprocess_ms, scan_ms, duplicate_ms, sort_ms, ranges_ms, blend_ms, total_ms;
     int num_rendered;
-    int sort_passes;
+    int sort_passes; /* depth passes + tile passes; sort_ms covers the tile passes only */
     int kernel_launches; /* kernels this library launched inside the call */
-    float sort_hist_ms;     /* up-front digit histograms (+ their scan) */
-    float sort_pass_ms[8];  /* each onesweep digit pass */
+    float sort_hist_ms;     /* digit-histogram scans of both sort halves (+ the depth-key histogram) */
+    float sort_pass_ms[8];  /* each onesweep digit pass: depth_passes passes over P Gaussians first,
+                               then the tile-digit passes over the num_rendered pairs */
+    float depth_sort_ms;    /* depth half of the LSD sort (P records), overlaps the num_rendered round trip */
+    int depth_passes;
 } gsr_stage_times;
 
 /* Same call with explicit strides / flags (superset of the two above). */
@@ -136,6 +139,15 @@ typedef struct gsr_geometry_state {
     uint32_t* point_offsets;  /* [P] inclusive scan of tiles_touched */
     uint32_t* block_sums;     /* scan scratch (replaces the CUB temp storage) */
     size_t scan_size;
+    /* depth half of the radix sort, run per Gaussian before duplication */
+    uint32_t* depth_keys;        /* [P] depth bits; 0xffffffff for Gaussians that emit no pair */
+    uint32_t* tile_rects;        /* [P][2] miny<<16|minx, height<<16|width of the tile rect (0 = emits nothing) */
+    uint32_t* depth_sort_keys[2];/* [P] ping-pong; [1] ends up holding the sorted depth keys */
+    uint32_t* depth_sort_ids[2]; /* [P] ping-pong; [1] ends up holding the Gaussian ids in depth order */
+    char* depth_sort_space;      /* histograms + look-back state of that sort */
+    size_t depth_sort_size;
+    uint32_t* dup_scan_state;    /* chained-scan words of the duplication kernel */
+    size_t dup_scan_size;
 } gsr_geometry_state;
 
 typedef struct gsr_image_state {
@@ -146,11 +158,11 @@ typedef struct gsr_image_state {
 } gsr_image_state;
 
 typedef struct gsr_binning_state {
-    uint64_t* point_list_keys_unsorted; /* [R] */
-    uint64_t* point_list_keys;          /* [R] sorted */
-    uint32_t* point_list_unsorted;      /* [R] */
+    uint64_t* point_list_keys_unsorted; /* [R] x 8 B: two ping-pong arrays of 32-bit tile keys */
+    uint64_t* point_list_keys;          /* [R] sorted (tile << 32 | depth bits) */
+    uint32_t* point_list_unsorted;      /* [R] Gaussian ids in depth-ordered emission order */
     uint32_t* point_list;               /* [R] sorted Gaussian ids */
-    char* list_sorting_space;           /* radix-sort histograms + look-back state */
+    char* list_sorting_space;           /* second id ping-pong array [R] + histograms + look-back state */
     size_t sorting_size;
 } gsr_binning_state;
 

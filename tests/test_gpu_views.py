@@ -29,7 +29,7 @@ def test_view_batch_matches_single_forward():
         assert np.array_equal(out[v].cpu().numpy(), single["out_color"])
         assert np.array_equal(host[v].numpy(), single["out_color"])
     out2, nr2, times = vr.render(cams[:2], cams[0].tan_fovx, cams[0].tan_fovy, timings=True)
-    assert times["num_rendered"] == nr2[1] and times["sort_passes"] >= 5 and times["kernel_launches"] >= 10
+    assert times["num_rendered"] == nr2[1] and times["sort_passes"] >= 5 and times["depth_passes"] == 4 and times["kernel_launches"] >= 10
     assert times["total_ms"] > 0
     vr.close()
 

@@ -73,7 +73,7 @@ class GeometryState(C.Structure):
                  "point_offsets", "block_sums")] + [("scan_size", C.c_size_t)] + \
                [("depth_keys", C.c_void_p), ("tile_rects", C.c_void_p), ("depth_sort_keys", C.c_void_p * 2), ("depth_sort_ids", C.c_void_p * 2),
                 ("depth_sort_space", C.c_void_p), ("depth_sort_size", C.c_size_t),
-                ("dup_scan_state", C.c_void_p), ("dup_scan_size", C.c_size_t)]
+                ("sorted_rects", C.c_void_p), ("sorted_block_sums", C.c_void_p)]
 
 
 class ImageState(C.Structure):

@@ -8,8 +8,9 @@
 // num_rendered comes from per-block sums (written by preprocess) and a single-CTA scan of those
 // sums (scan_block_sums_kernel, which publishes the total straight into mapped pinned host memory).
 // Duplication runs on the Gaussians in DEPTH order (they are radix-sorted by their depth key while
-// the host waits for num_rendered, see radix_sort.cu) with its own chained scan, is load-balanced
-// (the 256 Gaussians of a block pool their tile counts) and emits 32-bit tile keys.
+// the host waits for num_rendered, see radix_sort.cu): their tile rects are gathered into that order
+// and the per-block pair counts scanned in the same window; the duplication kernel itself is
+// load-balanced (the 256 Gaussians of a block pool their tile counts) and emits 32-bit tile keys.
 #include "gsr_common.cuh"
 
 namespace gsr {
@@ -17,6 +18,7 @@ namespace gsr {
 namespace {
 
 constexpr int SCAN_THREADS = 1024;
+constexpr int DUP_ITEMS = 4;  // consecutive outputs per thread and window in the duplication kernel
 
 // Exclusive scan of block_sums[n] in place; total -> *total_dev and *total_host (mapped).
 __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(uint32_t* __restrict__ block_sums, int n,
@@ -66,21 +68,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(uint32_t*
     }
 }
 
-// Status words of the chained scan carry flag and count in ONE 32-bit word (2 flag bits + 30-bit
-// count; num_rendered < 2^30 is enforced by the caller), so relaxed gpu-scope accesses suffice.
-constexpr uint32_t SCAN_AGG = 1u << 30;
-constexpr uint32_t SCAN_INC = 2u << 30;
-constexpr uint32_t SCAN_FLAGS = 3u << 30;
-
-__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
-    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 // Inclusive scan of tiles_touched in index order — the array cub::DeviceScan::InclusiveSum leaves in
 // pointOffsets (GSCuda.cu:771), which the Inspector reads (Inspector.cpp:174-188).  The pipeline itself
 // consumes the scan in depth order (duplicate_sorted_kernel), so this is materialised on the side.
@@ -106,16 +93,44 @@ __global__ void __launch_bounds__(PRE_THREADS) point_offsets_kernel(const int P,
     if (idx < P) point_offsets[idx] = block_offsets[blockIdx.x] + woff + incl;
 }
 
-// Duplication in depth order.  Block b (handed out by ticket, so predecessors have always started)
-// takes the 256 Gaussians sorted_ids[256b .. 256b+255], scans their tile counts, obtains its global
-// offset by a chained scan with decoupled look-back (warp 0 inspects 32 predecessors per step), and
-// emits every (tile, Gaussian) pair: rows outer, columns inner (GSCuda.cu:461-474).  The work is
-// pooled: the block's threads walk the pooled output range item by item, so one huge splat does not
-// serialise a thread and the stores are fully coalesced.  The digit histograms of the tile passes are
-// counted here (shared-memory atomics, flushed once per block), so the sort never re-reads the keys.
+// Gathers the tile rects into depth order (one 8-byte gather per Gaussian, then everything downstream
+// is coalesced) and leaves the per-block pair counts for the scan.  Runs while the host waits for
+// num_rendered.
+__global__ void __launch_bounds__(PRE_THREADS) gather_rects_kernel(const int P, const uint32_t* __restrict__ sorted_ids,
+                                                                   const uint2* __restrict__ tile_rects,
+                                                                   uint2* __restrict__ sorted_rects,
+                                                                   uint32_t* __restrict__ block_sums) {
+    __shared__ uint32_t s_warp[PRE_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = blockIdx.x * PRE_THREADS + tid;
+    uint32_t cnt = 0;
+    if (i < P) {
+        // the tile rect preprocess computed with getRect (GSCuda.cu:237-259; duplicateWithKeys recomputes the
+        // same rect, :445-458).  Gaussians that emit nothing (radii <= 0, :440-443) carry an empty rect.
+        const uint2 rec = __ldg(tile_rects + __ldg(sorted_ids + i));
+        sorted_rects[i] = rec;
+        cnt = (rec.y >> 16) * (rec.y & 0xffffu);
+    }
+    const uint32_t wsum = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0) s_warp[warp] = wsum;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int w = 0; w < PRE_THREADS / 32; ++w) t += s_warp[w];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+// Duplication in depth order.  Block b takes the 256 Gaussians at depth ranks 256b .. 256b+255, scans
+// their tile counts and emits every (tile, Gaussian) pair behind the block's scanned offset: rows
+// outer, columns inner (GSCuda.cu:461-474).  The work is pooled: the block's threads walk the pooled
+// output range item by item, so one huge splat does not serialise a thread and the stores are fully
+// coalesced.  The digit histograms of the tile passes are counted here (shared-memory atomics, flushed
+// once per block), so the sort never re-reads the keys.
 __global__ void __launch_bounds__(PRE_THREADS) duplicate_sorted_kernel(
-    const int P, const int grid_x, const uint32_t* __restrict__ sorted_ids, const uint2* __restrict__ tile_rects,
-    uint32_t* __restrict__ scan_state, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+    const int P, const int grid_x, const uint32_t* __restrict__ sorted_ids, const uint2* __restrict__ sorted_rects,
+    const uint32_t* __restrict__ block_offsets, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
     uint32_t* __restrict__ hist, const int tile_bits) {
     __shared__ uint32_t s_excl[PRE_THREADS + 1];
     __shared__ uint32_t s_warp[PRE_THREADS / 32];
@@ -123,24 +138,19 @@ __global__ void __launch_bounds__(PRE_THREADS) duplicate_sorted_kernel(
     __shared__ uint32_t s_origin[PRE_THREADS];  // miny << 16 | minx
     __shared__ uint32_t s_width[PRE_THREADS];
     __shared__ uint32_t s_hist[4 * 256];
-    __shared__ uint32_t s_ctl[2];  // block ticket, global offset
+    __shared__ __align__(16) uint32_t s_okey[DUP_ITEMS * PRE_THREADS];
+    __shared__ __align__(16) uint32_t s_oval[DUP_ITEMS * PRE_THREADS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int passes = (tile_bits + 7) >> 3;
-    if (tid == 0) s_ctl[0] = atomicAdd(scan_state, 1u);
-    for (int i = tid; i < passes * 256; i += PRE_THREADS) s_hist[i] = 0;
-    __syncthreads();
-    const uint32_t b = s_ctl[0];
-    uint32_t* status = scan_state + 2;
-    const int i = (int)b * PRE_THREADS + tid;
+    const int i = blockIdx.x * PRE_THREADS + tid;
     const bool valid = i < P;
-
-    // One 8-byte gather per Gaussian: the tile rect preprocess computed with getRect (GSCuda.cu:237-259;
-    // duplicateWithKeys recomputes the same rect, :445-458).  Gaussians that emit nothing (radii <= 0,
-    // GSCuda.cu:440-443) carry an empty rect and sort to the end (key 0xffffffff).
-    const uint32_t g = valid ? __ldg(sorted_ids + i) : 0u;
-    const uint2 rec = valid ? __ldg(tile_rects + g) : make_uint2(0u, 0u);
+    const uint2 rec = valid ? __ldg(sorted_rects + i) : make_uint2(0u, 0u);
     const uint32_t cnt = (rec.y >> 16) * (rec.y & 0xffffu);
+    const unsigned any = __ballot_sync(0xffffffffu, cnt != 0);
+    if (__syncthreads_or(any != 0) == 0) return;  // the culled tail of the depth order emits nothing
+    for (int j = tid; j < passes * 256; j += PRE_THREADS) s_hist[j] = 0;
+
     uint32_t incl = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -158,76 +168,83 @@ __global__ void __launch_bounds__(PRE_THREADS) duplicate_sorted_kernel(
     incl += woff;
     s_excl[tid] = incl - cnt;
     if (tid == PRE_THREADS - 1) s_excl[PRE_THREADS] = incl;
-
-    // ---- chained scan across blocks ---------------------------------------------------------
-    if (warp == 0) {
-        if (lane == 0) st_relaxed_u32(status + b, (b == 0 ? SCAN_INC : SCAN_AGG) | total);
-        uint32_t excl = 0;
-        if (b > 0) {
-            int64_t t = (int64_t)b - 1;
-            uint32_t spins = 0;
-            while (true) {
-                const int64_t idx = t - lane;
-                uint32_t v = SCAN_INC;  // before the first block: inclusive prefix 0
-                if (idx >= 0) {
-                    v = ld_relaxed_u32(status + idx);
-                    while ((v & SCAN_FLAGS) == 0) {
-                        if (++spins > (1u << 22)) {  // watchdog: never expected to trip
-                            atomicExch(scan_state + 1, 1u);
-                            v = SCAN_INC;
-                            break;
-                        }
-                        __nanosleep(20);
-                        v = ld_relaxed_u32(status + idx);
-                    }
-                }
-                const unsigned inc = __ballot_sync(0xffffffffu, (v & SCAN_FLAGS) == SCAN_INC);
-                const int first = inc ? (__ffs(inc) - 1) : 32;
-                excl += __reduce_add_sync(0xffffffffu, (lane <= first) ? (v & ~SCAN_FLAGS) : 0u);
-                if (inc) break;
-                t -= 32;
-            }
-            if (lane == 0) st_relaxed_u32(status + b, SCAN_INC | (excl + total));
-        }
-        if (lane == 0) s_ctl[1] = excl;
-    }
-
     if (cnt > 0) {
-        s_gid[tid] = g;
+        s_gid[tid] = __ldg(sorted_ids + i);
         s_origin[tid] = rec.x;
         s_width[tid] = rec.y & 0xffffu;
     }
     __syncthreads();
 
-    const uint32_t boff = s_ctl[1];
-    for (uint32_t k = tid; k < total; k += PRE_THREADS) {
-        // largest j with s_excl[j] <= k
-        int lo = 0, hi = PRE_THREADS - 1;
+    const uint32_t boff = block_offsets[blockIdx.x];
+    const uint32_t lowmask = (1u << min(8, tile_bits)) - 1u;
+    // Windows of 4*256 outputs: thread t produces outputs 4t..4t+3 of the window (one binary search, then
+    // a walk along the rect rows), the window is transposed through shared memory and stored coalesced.
+    for (uint32_t kb = 0; kb < total; kb += DUP_ITEMS * PRE_THREADS) {
+        const uint32_t k0 = kb + DUP_ITEMS * tid;
+        uint32_t okey[DUP_ITEMS], oval[DUP_ITEMS];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (s_excl[mid] <= k) lo = mid; else hi = mid - 1;
+        for (int j = 0; j < DUP_ITEMS; ++j) okey[j] = oval[j] = 0;
+        if (k0 < total) {
+            // largest j with s_excl[j] <= k0
+            int lo = 0, hi = PRE_THREADS - 1;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (s_excl[mid] <= k0) lo = mid; else hi = mid - 1;
+            }
+            uint32_t w = s_width[lo], org = s_origin[lo], gid = s_gid[lo], next = s_excl[lo + 1];
+            const uint32_t t = k0 - s_excl[lo];
+            const uint32_t ty = t / w;
+            uint32_t tx = t - ty * w;
+            uint32_t row_tile = ((org >> 16) + ty) * (uint32_t)grid_x + (org & 0xffffu);
+            uint32_t run_d = 0xffffffffu, run_n = 0;  // run of equal second digits inside this thread
+#pragma unroll
+            for (int j = 0; j < DUP_ITEMS; ++j) {
+                const uint32_t k = k0 + j;
+                if (k < total) {
+                    if (k >= next) {  // next Gaussian that emits anything (empty ones have equal offsets)
+                        do { ++lo; next = s_excl[lo + 1]; } while (k >= next);
+                        w = s_width[lo]; org = s_origin[lo]; gid = s_gid[lo];
+                        tx = 0;
+                        row_tile = (org >> 16) * (uint32_t)grid_x + (org & 0xffffu);
+                    }
+                    // key = tile id (GSCuda.cu:466-471: the depth half is re-attached by the last sort pass)
+                    const uint32_t tile = row_tile + tx;
+                    okey[j] = tile; oval[j] = gid;
+                    if (++tx == w) { tx = 0; row_tile += (uint32_t)grid_x; }
+                    atomicAdd(&s_hist[tile & lowmask], 1u);
+                    if (passes > 1) {
+                        const uint32_t d = (tile >> 8) & ((1u << min(8, tile_bits - 8)) - 1u);
+                        if (d != run_d) {
+                            if (run_n) atomicAdd(&s_hist[256 + run_d], run_n);
+                            run_d = d; run_n = 0;
+                        }
+                        ++run_n;
+                        for (int ps = 2; ps < passes; ++ps)
+                            atomicAdd(&s_hist[ps * 256 + ((tile >> (8 * ps)) & ((1u << min(8, tile_bits - 8 * ps)) - 1u))], 1u);
+                    }
+                }
+            }
+            if (run_n) atomicAdd(&s_hist[256 + run_d], run_n);
         }
-        const uint32_t t = k - s_excl[lo];
-        const uint32_t w = s_width[lo];
-        const uint32_t ty = t / w, tx = t - ty * w;
-        const uint32_t org = s_origin[lo];
-        // key = tile id (GSCuda.cu:466-471: the depth half is re-attached by the last sort pass)
-        const uint32_t tile = ((org >> 16) + ty) * (uint32_t)grid_x + (org & 0xffffu) + tx;
-        const size_t o = (size_t)boff + k;
-        keys_out[o] = tile;
-        vals_out[o] = s_gid[lo];
-        for (int ps = 0; ps < passes; ++ps) {
-            const int nb = min(8, tile_bits - 8 * ps);
-            atomicAdd(&s_hist[ps * 256 + ((tile >> (8 * ps)) & ((1u << nb) - 1u))], 1u);
+        reinterpret_cast<uint4*>(s_okey)[tid] = make_uint4(okey[0], okey[1], okey[2], okey[3]);
+        reinterpret_cast<uint4*>(s_oval)[tid] = make_uint4(oval[0], oval[1], oval[2], oval[3]);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < DUP_ITEMS; ++j) {
+            const uint32_t q = tid + j * PRE_THREADS;
+            if (kb + q < total) {
+                const size_t o = (size_t)boff + kb + q;
+                keys_out[o] = s_okey[q];
+                vals_out[o] = s_oval[q];
+            }
         }
+        __syncthreads();
     }
     __syncthreads();
-    if (total > 0) {
-        for (int j = tid; j < passes * 256; j += PRE_THREADS) {
-            const uint32_t c = s_hist[j];
-            if (c) atomicAdd(hist + j, c);
-        }
+    for (int j = tid; j < passes * 256; j += PRE_THREADS) {
+        const uint32_t c = s_hist[j];
+        if (c) atomicAdd(hist + j, c);
     }
 }
 
@@ -285,19 +302,24 @@ int launch_point_offsets(int P, const uint32_t* tiles_touched, const uint32_t* b
     return e == cudaSuccess ? 1 : -(int)e;
 }
 
-size_t dup_scan_state_bytes(int P) {
-    const size_t blocks = (size_t)((P > 0 ? P : 0) + PRE_THREADS - 1) / PRE_THREADS;
-    return (blocks + 2 + 30) / 32 * 32 * sizeof(uint32_t);
+int launch_gather_rects(int P, const uint32_t* sorted_ids, const uint32_t* tile_rects, uint32_t* sorted_rects,
+                        uint32_t* block_sums, cudaStream_t s) {
+    if (P <= 0) return 0;
+    const int blocks = (P + PRE_THREADS - 1) / PRE_THREADS;
+    gather_rects_kernel<<<blocks, PRE_THREADS, 0, s>>>(P, sorted_ids, reinterpret_cast<const uint2*>(tile_rects),
+                                                       reinterpret_cast<uint2*>(sorted_rects), block_sums);
+    cudaError_t e = cudaPeekAtLastError();
+    return e == cudaSuccess ? 1 : -(int)e;
 }
 
-int launch_duplicate_sorted(int P, int grid_x, const uint32_t* sorted_ids, const uint32_t* tile_rects,
-                            uint32_t* scan_state, uint32_t* keys32_out, uint32_t* vals_out, uint32_t* hist,
+int launch_duplicate_sorted(int P, int grid_x, const uint32_t* sorted_ids, const uint32_t* sorted_rects,
+                            const uint32_t* block_offsets, uint32_t* keys32_out, uint32_t* vals_out, uint32_t* hist,
                             int tile_bits, cudaStream_t s) {
     if (P <= 0) return 0;
     if (tile_bits < 1 || tile_bits > 32) return GSR_ERR_INVALID_ARG;
     const int blocks = (P + PRE_THREADS - 1) / PRE_THREADS;
     duplicate_sorted_kernel<<<blocks, PRE_THREADS, 0, s>>>(P, grid_x, sorted_ids,
-                                                           reinterpret_cast<const uint2*>(tile_rects), scan_state,
+                                                           reinterpret_cast<const uint2*>(sorted_rects), block_offsets,
                                                            keys32_out, vals_out, hist, tile_bits);
     cudaError_t e = cudaPeekAtLastError();
     return e == cudaSuccess ? 1 : -(int)e;

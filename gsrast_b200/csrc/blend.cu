@@ -11,11 +11,12 @@
 //                        pixel per thread) with the block-wide early exit; kept for A/B.
 //   blend_culled_kernel  default.  Each warp owns an 8x4-pixel sub-rectangle of the tile.
 //                        While a batch is staged, the staging thread of every splat computes
-//                        exactly-conservatively which of the 8 sub-rectangles the splat can
-//                        reach with alpha >= 1/255 (maximum of the concave quadratic `power`
-//                        over the rectangle); each warp then walks only its own survivors,
-//                        found with warp ballots, and leaves the batch loop as soon as its 32
-//                        pixels have saturated (__all_sync), independently of the other warps.
+//                        conservatively which of the 8 sub-rectangles the splat can reach with
+//                        alpha >= 1/255 (bounding box of the alpha >= 1/255 ellipse, refined by the
+//                        maximum of the concave quadratic `power` over the rectangle); each warp
+//                        compacts its own survivors with warp ballots into a private index list,
+//                        walks only those, and leaves the batch loop as soon as its 32 pixels
+//                        have saturated (__all_sync), independently of the other warps.
 // There is no dense contraction here, hence no tensor cores: the work is FP32 FMA + MUFU.EX2
 // issue and shared-memory broadcast bandwidth.
 #include "gsr_common.cuh"
@@ -121,11 +122,14 @@ __device__ __forceinline__ float max_power_in_box(float a, float b, float c, flo
     return fmaxf(f1, f2);
 }
 
+// Staged splat record: 48 bytes, three 16-byte shared loads off one base address.
+//   [0] x, y, a', b'      (conic pre-scaled by log2(e): power*log2(e) = a' dx^2 + c' dy^2 + b' dx dy)
+//   [1] c', opacity, r, g
+//   [2] b, -, -, -
 __global__ void __launch_bounds__(BLEND_THREADS) blend_culled_kernel(const BlendParams p) {
-    __shared__ float4 s_a[BATCH];      // x, y, a', b'      (conic pre-scaled by log2(e): see below)
-    __shared__ float4 s_b[BATCH];      // c', opacity, r, g
-    __shared__ float s_c[BATCH];       // b
-    __shared__ uint32_t s_mask[BATCH]; // bit w: splat can reach warp w's 8x4 sub-rectangle
+    __shared__ float4 s_splat[BATCH * 3];
+    __shared__ unsigned char s_mask[BATCH];                     // bit w: splat can reach warp w's 8x4 sub-rectangle
+    __shared__ unsigned char s_list[BLEND_THREADS / 32][BATCH]; // per warp: staged indices of its candidates
 
     const int tile = p.tile_order ? (int)__ldg(p.tile_order + blockIdx.x) : (int)blockIdx.x;
     const int tile_x = tile % p.grid_x, tile_y = tile / p.grid_x;
@@ -136,6 +140,8 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_culled_kernel(const Blend
     const bool inside = pix_x < p.W && pix_y < p.H;
     const float pixf_x = (float)pix_x, pixf_y = (float)pix_y;
     const float tile_x0 = (float)(tile_x * TILE_X), tile_y0 = (float)(tile_y * TILE_Y);
+    const uint32_t lane_lt = (1u << lane) - 1u;
+    unsigned char* my_list = s_list[warp];
 
     const uint2 range = reinterpret_cast<const uint2*>(p.ranges)[tile];
     const int total = (int)(range.y - range.x);
@@ -156,13 +162,14 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_culled_kernel(const Blend
             const float4 co = __ldg(reinterpret_cast<const float4*>(p.conic_opacity) + id);
             const float* col = p.colors + (size_t)id * 3;
             const float a = co.x, b = co.y, c = co.z, o = co.w;
-            // power*log2(e) = a' dx^2 + c' dy^2 + b' dx dy  with a' = -0.5 a log2e, ...
-            s_a[tid] = make_float4(xy.x, xy.y, -0.5f * LOG2E * a, -LOG2E * b);
-            s_b[tid] = make_float4(-0.5f * LOG2E * c, o, __ldg(col), __ldg(col + 1));
-            s_c[tid] = __ldg(col + 2);
+            s_splat[3 * tid + 0] = make_float4(xy.x, xy.y, -0.5f * LOG2E * a, -LOG2E * b);
+            s_splat[3 * tid + 1] = make_float4(-0.5f * LOG2E * c, o, __ldg(col), __ldg(col + 1));
+            s_splat[3 * tid + 2] = make_float4(__ldg(col + 2), 0.f, 0.f, 0.f);
             // ---- which sub-rectangles can see this splat with alpha >= 1/255 ? ----------
-            // alpha >= 1/255  <=>  power >= -ln(255*o).  Keep a small slack so float rounding in
-            // the bound can only add work, never drop a contributing splat.
+            // alpha >= 1/255  <=>  power >= -ln(255*o) =: thr.  First the axis-aligned bounding box of that
+            // ellipse (half extents sqrt(-2 thr c/det), sqrt(-2 thr a/det)) picks candidate sub-rectangles,
+            // then the exact maximum of `power` over each candidate decides.  Slack everywhere so float
+            // rounding in the bounds can only add work, never drop a contributing splat.
             const float det = a * c - b * b;
             if (!(o >= ALPHA_MIN * 0.999f)) {
                 m = 0;  // exp(power) <= 1  =>  alpha < 1/255 everywhere (also catches NaN opacity)
@@ -170,30 +177,53 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_culled_kernel(const Blend
                 m = 0xffu;  // degenerate conic: no culling
             } else {
                 const float thr = -__logf(255.0f * o) * 1.0001f - 1e-3f;
-                const float mba = -b / a, mbc = -b / c;
-                // dx = x - px, px in [X, X+w-1]  ->  dx in [x - (X+w-1), x - X]
-                const float bx1 = xy.x - tile_x0, by1 = xy.y - tile_y0;
-                if (max_power_in_box(a, b, c, mba, mbc, bx1 - 15.f, bx1, by1 - 15.f, by1) >= thr) {
+                const float sc = __fdividef(-2.0f * thr, det);
+                const float ex = sqrtf(sc * c) * 1.0001f + 0.01f, ey = sqrtf(sc * a) * 1.0001f + 0.01f;
+                const float bx1 = xy.x - tile_x0, by1 = xy.y - tile_y0;  // centre relative to the tile origin
+                const float xlo = bx1 - ex, xhi = bx1 + ex, ylo = by1 - ey, yhi = by1 + ey;
+                if (!(ex < 1e7f) || !(ey < 1e7f)) {
+                    m = 0xffu;
+                } else {
+                    const uint32_t colm = ((xlo <= 7.f && xhi >= 0.f) ? 1u : 0u) | ((xlo <= 15.f && xhi >= 8.f) ? 2u : 0u);
+                    uint32_t cand = 0;
 #pragma unroll
-                    for (int w = 0; w < 8; ++w) {
-                        const float wx1 = bx1 - (float)((w & 1) << 3), wy1 = by1 - (float)((w >> 1) << 2);
-                        if (max_power_in_box(a, b, c, mba, mbc, wx1 - 7.f, wx1, wy1 - 3.f, wy1) >= thr) m |= 1u << w;
+                    for (int rr = 0; rr < 4; ++rr)
+                        if (ylo <= (float)(4 * rr + 3) && yhi >= (float)(4 * rr)) cand |= colm << (2 * rr);
+                    if (cand) {
+                        const float mba = -b / a, mbc = -b / c;
+                        while (cand) {
+                            const int w = __ffs(cand) - 1;
+                            cand &= cand - 1;
+                            // dx = x - px, px in [X, X+7]  ->  dx in [x - (X+7), x - X]
+                            const float wx1 = bx1 - (float)((w & 1) << 3), wy1 = by1 - (float)((w >> 1) << 2);
+                            if (max_power_in_box(a, b, c, mba, mbc, wx1 - 7.f, wx1, wy1 - 3.f, wy1) >= thr) m |= 1u << w;
+                        }
                     }
                 }
             }
         }
-        s_mask[tid] = m;
+        s_mask[tid] = (unsigned char)m;
         __syncthreads();
 
         if (!warp_done) {
-            const int nb = min(BATCH, total - r * BATCH);
-            for (int c0 = 0; c0 < nb; c0 += 32) {
-                unsigned bits = __ballot_sync(0xffffffffu, (s_mask[c0 + lane] >> warp) & 1u);
-                while (bits) {
-                    const int j = c0 + __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    const float4 a = s_a[j];
-                    const float4 b = s_b[j];
+            // this warp's candidates of the batch, in order
+            int n = 0;
+#pragma unroll
+            for (int c0 = 0; c0 < BATCH; c0 += 32) {
+                const bool mine = (s_mask[c0 + lane] >> warp) & 1u;
+                const unsigned bits = __ballot_sync(0xffffffffu, mine);
+                if (mine) my_list[n + __popc(bits & lane_lt)] = (unsigned char)(c0 + lane);
+                n += __popc(bits);
+            }
+            __syncwarp();
+            const uint32_t rbase = (uint32_t)(r * BATCH + 1);
+            for (int i0 = 0; i0 < n; i0 += 16) {
+                const int i1 = min(n, i0 + 16);
+                for (int i = i0; i < i1; ++i) {
+                    const int j = my_list[i];
+                    const float4* sp = s_splat + 3 * j;
+                    const float4 a = sp[0];
+                    const float4 b = sp[1];
                     const float dx = a.x - pixf_x, dy = a.y - pixf_y;
                     const float p2 = fmaf(a.z, dx * dx, fmaf(b.x, dy * dy, a.w * (dx * dy)));
                     const float alpha = fminf(0.99f, b.y * ex2_approx(p2));
@@ -206,9 +236,9 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_culled_kernel(const Blend
                     const float w = alpha * T;
                     C0 = fmaf(b.z, w, C0);
                     C1 = fmaf(b.w, w, C1);
-                    C2 = fmaf(s_c[j], w, C2);
+                    C2 = fmaf(sp[2].x, w, C2);
                     T = test_T;
-                    last = (uint32_t)(r * BATCH + j + 1);
+                    last = rbase + (uint32_t)j;
                 }
                 if (__all_sync(0xffffffffu, done)) {
                     warp_done = true;

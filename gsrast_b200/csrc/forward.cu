@@ -141,8 +141,8 @@ size_t gsr_geometry_state_map(char* chunk, int P, gsr_geometry_state* g) {
     for (int i = 0; i < 2; ++i) obtain(c, st.depth_sort_ids[i], n * sizeof(uint32_t));
     st.depth_sort_size = sort_temp_bytes(n);
     obtain(c, st.depth_sort_space, st.depth_sort_size);
-    st.dup_scan_size = dup_scan_state_bytes(P);
-    obtain(c, st.dup_scan_state, st.dup_scan_size);
+    obtain(c, st.sorted_rects, n * 2 * sizeof(uint32_t));
+    obtain(c, st.sorted_block_sums, st.scan_size);
     if (g) *g = st;
     return (size_t)(c - chunk);
 }
@@ -293,9 +293,11 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         dp.keys_out = geom.depth_sort_keys[1]; dp.vals_out = geom.depth_sort_ids[1];
         dp.temp = geom.depth_sort_space; dp.hist_ready = false;
         GSR_STAGE(launch_sort32(dp, s, sort_timed ? sort_ev : nullptr));
+        // tile rects into depth order + scan of the per-block pair counts (same total, other order)
+        GSR_STAGE(launch_gather_rects(P, geom.depth_sort_ids[1], geom.tile_rects, geom.sorted_rects,
+                                      geom.sorted_block_sums, s));
+        GSR_STAGE(launch_scan_block_sums(geom.sorted_block_sums, nb, geom.sorted_block_sums + nb, nullptr, s));
         GSR_STAGE(launch_point_offsets(P, geom.tiles_touched, geom.block_sums, geom.point_offsets, s));
-        e = cudaMemsetAsync(geom.dup_scan_state, 0, geom.dup_scan_size, s);
-        if (e != cudaSuccess) GSR_FAIL(-(int)e);
         tm.mark();  // 3
         // the one host round trip: num_rendered decides the binning allocation (GSCuda.cu:772,782)
         e = cudaEventSynchronize(slot.landed);
@@ -336,7 +338,7 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
     char* tile_temp = bin.list_sorting_space + ((size_t)R * sizeof(uint32_t) + 127) / 128 * 128;
     uint32_t* tile_hist = sort32_prepare(tile_temp, (size_t)R, tile_bits, s);
     if (!tile_hist) GSR_FAIL(-(int)cudaGetLastError());
-    GSR_STAGE(launch_duplicate_sorted(P, gx, geom.depth_sort_ids[1], geom.tile_rects, geom.dup_scan_state, k32[0],
+    GSR_STAGE(launch_duplicate_sorted(P, gx, geom.depth_sort_ids[1], geom.sorted_rects, geom.sorted_block_sums, k32[0],
                                       v32[0], tile_hist, tile_bits, s));
     tm.mark();  // 4
     {

@@ -70,13 +70,15 @@ int launch_scan_block_sums(uint32_t* block_sums, int num_blocks, uint32_t* total
 // already hold the exclusive block offsets.
 int launch_point_offsets(int P, const uint32_t* tiles_touched, const uint32_t* block_sums, uint32_t* point_offsets,
                          cudaStream_t s);
-// Emits the (tile, Gaussian) pairs of the Gaussians taken in the order `sorted_ids` (ascending depth
-// key): 32-bit tile keys + Gaussian ids, and accumulates the tile-digit histograms of the following
-// radix passes into `hist` ([passes][256], zeroed).  `scan_state` = num_dup_blocks(P)+2 zeroed words.
-int launch_duplicate_sorted(int P, int grid_x, const uint32_t* sorted_ids, const uint32_t* tile_rects,
-                            uint32_t* scan_state, uint32_t* keys32_out, uint32_t* vals_out, uint32_t* hist,
+// sorted_rects[i] = tile_rects[sorted_ids[i]] and block_sums[b] = pairs emitted by depth ranks 256b..256b+255.
+int launch_gather_rects(int P, const uint32_t* sorted_ids, const uint32_t* tile_rects, uint32_t* sorted_rects,
+                        uint32_t* block_sums, cudaStream_t s);
+// Emits the (tile, Gaussian) pairs of the Gaussians taken in depth order: 32-bit tile keys + Gaussian
+// ids, and accumulates the tile-digit histograms of the following radix passes into `hist`
+// ([passes][256], zeroed).  `block_offsets` = exclusive scan of launch_gather_rects' block_sums.
+int launch_duplicate_sorted(int P, int grid_x, const uint32_t* sorted_ids, const uint32_t* sorted_rects,
+                            const uint32_t* block_offsets, uint32_t* keys32_out, uint32_t* vals_out, uint32_t* hist,
                             int tile_bits, cudaStream_t s);
-size_t dup_scan_state_bytes(int P);
 int launch_identify_ranges(const uint64_t* keys, size_t n, uint32_t* ranges, int num_tiles, bool compat,
                            cudaStream_t s);
 

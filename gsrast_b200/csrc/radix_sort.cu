@@ -40,9 +40,11 @@ namespace {
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
 constexpr int SORT_THREADS = 256;  // == RADIX: thread d owns digit d in the scan / look-back steps
-constexpr int SORT_ITEMS = 16;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 pairs
+// Items per thread: 16 (4096-pair tiles) for the big pair-level passes, 8 for the Gaussian-level
+// depth passes, whose few hundred tiles would otherwise not fill the machine twice.
+constexpr int ITEMS_LARGE = 16;
+constexpr int ITEMS_SMALL = 8;
 constexpr int MAX_PASSES = 8;
 #ifndef GSR_LOOKBACK_W
 #define GSR_LOOKBACK_W 8
@@ -165,14 +167,15 @@ struct PassArgs {
 
 // Shared memory: [SORT_TILE] key staging | [SORT_TILE] u32 value staging | per-warp digit counters
 // [SORT_WARPS][RADIX] | per-warp match masks [SORT_WARPS][RADIX] | global bases [RADIX] | misc[16].
-template <typename KeyT>
+template <typename KeyT, int SORT_ITEMS>
 constexpr size_t onesweep_smem() {
-    return (size_t)SORT_TILE * (sizeof(KeyT) + 4) + (size_t)(2 * SORT_WARPS * RADIX + RADIX + 16) * 4;
+    return (size_t)SORT_THREADS * SORT_ITEMS * (sizeof(KeyT) + 4) + (size_t)(2 * SORT_WARPS * RADIX + RADIX + 16) * 4;
 }
 
-template <typename KeyT, bool EXPAND, bool FULL>
+template <typename KeyT, bool EXPAND, bool FULL, int SORT_ITEMS>
 __device__ __forceinline__ void onesweep_tile(const PassArgs& a, const uint32_t n_tile, const uint32_t tile,
                                               unsigned char* s_raw) {
+    constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
     KeyT* s_keys = reinterpret_cast<KeyT*>(s_raw);                                             // [SORT_TILE]
     uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_raw + (size_t)SORT_TILE * sizeof(KeyT));  // [SORT_TILE]
     uint32_t* s_whist = s_vals + SORT_TILE;                                                    // [2][SORT_WARPS][RADIX]
@@ -354,8 +357,9 @@ __device__ __forceinline__ void onesweep_tile(const PassArgs& a, const uint32_t 
     }
 }
 
-template <typename KeyT, bool EXPAND, int MIN_BLOCKS>
+template <typename KeyT, bool EXPAND, int MIN_BLOCKS, int SORT_ITEMS>
 __global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) onesweep_kernel(const PassArgs a) {
+    constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
     extern __shared__ __align__(16) unsigned char s_raw[];
     uint32_t* s_whist = reinterpret_cast<uint32_t*>(s_raw + (size_t)SORT_TILE * (sizeof(KeyT) + 4));
     uint32_t* s_misc = s_whist + 2 * SORT_WARPS * RADIX + RADIX;
@@ -368,12 +372,12 @@ __global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) onesweep_kernel(cons
     const size_t tile_base = (size_t)tile * SORT_TILE;
     const uint32_t n_tile = (uint32_t)min((size_t)SORT_TILE, a.n - tile_base);
     if (n_tile == SORT_TILE)
-        onesweep_tile<KeyT, EXPAND, true>(a, n_tile, tile, s_raw);
+        onesweep_tile<KeyT, EXPAND, true, SORT_ITEMS>(a, n_tile, tile, s_raw);
     else
-        onesweep_tile<KeyT, EXPAND, false>(a, n_tile, tile, s_raw);
+        onesweep_tile<KeyT, EXPAND, false, SORT_ITEMS>(a, n_tile, tile, s_raw);
 }
 
-size_t num_sort_tiles(size_t n) { return (n + SORT_TILE - 1) / SORT_TILE; }
+size_t num_sort_tiles(size_t n, int items) { return (n + (size_t)SORT_THREADS * items - 1) / ((size_t)SORT_THREADS * items); }
 
 struct TempLayout {
     uint32_t* hist;     // [MAX_PASSES][RADIX]  global digit histograms -> exclusive offsets
@@ -382,7 +386,7 @@ struct TempLayout {
     size_t zero_bytes;
 };
 
-TempLayout carve_temp(char* temp, size_t n, int passes) {
+TempLayout carve_temp(char* temp, size_t n, int passes, int items) {
     TempLayout L;
     char* t = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(temp), 128));
     L.hist = reinterpret_cast<uint32_t*>(t);
@@ -391,7 +395,7 @@ TempLayout carve_temp(char* temp, size_t n, int passes) {
     t += align_up((size_t)MAX_PASSES * 2 * 4, 128);
     L.status = reinterpret_cast<uint32_t*>(t);
     L.zero_bytes = (size_t)(reinterpret_cast<char*>(L.status) - reinterpret_cast<char*>(L.hist)) +
-                   (size_t)passes * num_sort_tiles(n) * RADIX * 4;
+                   (size_t)passes * num_sort_tiles(n, items) * RADIX * 4;
     return L;
 }
 
@@ -417,15 +421,21 @@ int launch_histogram(const KeyT* keys, size_t n, int end_bit, int passes, uint32
     return 1;
 }
 
-template <typename KeyT, bool EXPAND, int MIN_BLOCKS>
+template <typename KeyT, bool EXPAND, int MIN_BLOCKS, int ITEMS>
 int launch_pass(const PassArgs& a, cudaStream_t s) {
-    constexpr size_t smem = onesweep_smem<KeyT>();
+    constexpr size_t smem = onesweep_smem<KeyT, ITEMS>();
     // per-device attribute; cheap enough to set on every call (one process may drive several GPUs)
-    GSR_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS>,
+    GSR_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS, ITEMS>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS><<<(unsigned)num_sort_tiles(a.n), SORT_THREADS, smem, s>>>(a);
+    onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS, ITEMS><<<(unsigned)num_sort_tiles(a.n, ITEMS), SORT_THREADS, smem, s>>>(a);
     return 1;
 }
+
+// Small inputs get small tiles (more CTAs, shorter per-CTA dependency chains).
+#ifndef GSR_SMALL_N_LOG2
+#define GSR_SMALL_N_LOG2 0
+#endif
+inline int sort32_items(size_t n) { return n < ((size_t)1 << GSR_SMALL_N_LOG2) ? ITEMS_SMALL : ITEMS_LARGE; }
 
 }  // namespace
 
@@ -435,7 +445,8 @@ size_t sort_temp_bytes(size_t n) {
     size_t b = 0;
     b += align_up((size_t)MAX_PASSES * RADIX * 4, 128);
     b += align_up((size_t)MAX_PASSES * 2 * 4, 128);
-    b += align_up((size_t)MAX_PASSES * num_sort_tiles(n) * RADIX * 4, 128);
+    // 8 passes of large tiles (64-bit keys) >= 4 passes of small tiles (32-bit keys): same bytes + rounding
+    b += align_up((size_t)MAX_PASSES * (num_sort_tiles(n, ITEMS_LARGE) + 1) * RADIX * 4, 128);
     return b + 128;
 }
 
@@ -447,8 +458,8 @@ int launch_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint
     if (n == 0) return 0;
     if (passes < 1 || passes > MAX_PASSES || end_bit > 64) return GSR_ERR_INVALID_ARG;
     if (n >= ((size_t)1 << 30)) return GSR_ERR_TOO_MANY_PAIRS;
-    const size_t tiles = num_sort_tiles(n);
-    TempLayout L = carve_temp(temp, n, passes);
+    const size_t tiles = num_sort_tiles(n, ITEMS_LARGE);
+    TempLayout L = carve_temp(temp, n, passes, ITEMS_LARGE);
     GSR_CUDA_TRY(cudaMemsetAsync(L.hist, 0, L.zero_bytes, s));
 
     int launches = 0;
@@ -469,7 +480,7 @@ int launch_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint
         a.ticket = L.tickets + ps;
         a.error_flag = L.tickets + MAX_PASSES;
         a.expand_low = nullptr; a.keys_out64 = nullptr;
-        int rc = launch_pass<uint2, false, 2>(a, s);
+        int rc = launch_pass<uint2, false, 2, ITEMS_LARGE>(a, s);
         if (rc < 0) return rc;
         ++launches;
         if (events) cudaEventRecord(events[2 + ps], s);
@@ -484,7 +495,7 @@ int launch_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint
 // ---- 32-bit-key sort used by the forward path --------------------------------------------------
 uint32_t* sort32_prepare(char* temp, size_t n, int end_bit, cudaStream_t s) {
     const int passes = sort_num_passes(end_bit);
-    TempLayout L = carve_temp(temp, n, passes);
+    TempLayout L = carve_temp(temp, n, passes, sort32_items(n));
     if (cudaMemsetAsync(L.hist, 0, L.zero_bytes, s) != cudaSuccess) return nullptr;
     return L.hist;
 }
@@ -494,8 +505,9 @@ int launch_sort32(const Sort32Plan& p, cudaStream_t s, cudaEvent_t* events) {
     if (p.n == 0) return 0;
     if (passes < 1 || passes > 4 || p.end_bit > 32) return GSR_ERR_INVALID_ARG;
     if (p.n >= ((size_t)1 << 30)) return GSR_ERR_TOO_MANY_PAIRS;
-    const size_t tiles = num_sort_tiles(p.n);
-    TempLayout L = carve_temp(p.temp, p.n, passes);
+    const int items = sort32_items(p.n);
+    const size_t tiles = num_sort_tiles(p.n, items);
+    TempLayout L = carve_temp(p.temp, p.n, passes, items);
     int launches = 0;
     if (events) cudaEventRecord(events[0], s);
     if (!p.hist_ready) {
@@ -522,13 +534,16 @@ int launch_sort32(const Sort32Plan& p, cudaStream_t s, cudaEvent_t* events) {
             a.keys_out = p.keys_out; a.vals_out = p.vals_out;
             if (p.expand_low) {
                 a.expand_low = p.expand_low; a.keys_out64 = p.keys_out64;
-                rc = launch_pass<uint32_t, true, 3>(a, s);
+                rc = items == ITEMS_SMALL ? launch_pass<uint32_t, true, 4, ITEMS_SMALL>(a, s)
+                                          : launch_pass<uint32_t, true, 3, ITEMS_LARGE>(a, s);
             } else {
-                rc = launch_pass<uint32_t, false, 4>(a, s);
+                rc = items == ITEMS_SMALL ? launch_pass<uint32_t, false, 6, ITEMS_SMALL>(a, s)
+                                          : launch_pass<uint32_t, false, 4, ITEMS_LARGE>(a, s);
             }
         } else {
             a.keys_out = p.kbuf[ps & 1]; a.vals_out = p.vbuf[ps & 1];
-            rc = launch_pass<uint32_t, false, 4>(a, s);
+            rc = items == ITEMS_SMALL ? launch_pass<uint32_t, false, 6, ITEMS_SMALL>(a, s)
+                                      : launch_pass<uint32_t, false, 4, ITEMS_LARGE>(a, s);
             kin = p.kbuf[ps & 1]; vin = p.vbuf[ps & 1];
         }
         if (rc < 0) return rc;

@@ -146,8 +146,8 @@ typedef struct gsr_geometry_state {
     uint32_t* depth_sort_ids[2]; /* [P] ping-pong; [1] ends up holding the Gaussian ids in depth order */
     char* depth_sort_space;      /* histograms + look-back state of that sort */
     size_t depth_sort_size;
-    uint32_t* dup_scan_state;    /* chained-scan words of the duplication kernel */
-    size_t dup_scan_size;
+    uint32_t* sorted_rects;      /* [P][2] tile_rects gathered into depth order */
+    uint32_t* sorted_block_sums; /* scan scratch of the pair counts in depth order (scan_size bytes) */
 } gsr_geometry_state;
 
 typedef struct gsr_image_state {

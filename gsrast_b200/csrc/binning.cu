@@ -19,6 +19,8 @@ namespace {
 
 constexpr int SCAN_THREADS = 1024;
 constexpr int DUP_ITEMS = 4;  // consecutive outputs per thread and window in the duplication kernel
+constexpr int DUP_GPT = 4;    // Gaussians (consecutive depth ranks) per thread of a duplication block
+constexpr int DUP_GAUSS = DUP_GPT * PRE_THREADS;
 
 // Exclusive scan of block_sums[n] in place; total -> *total_dev and *total_host (mapped).
 __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(uint32_t* __restrict__ block_sums, int n,
@@ -94,22 +96,25 @@ __global__ void __launch_bounds__(PRE_THREADS) point_offsets_kernel(const int P,
 }
 
 // Gathers the tile rects into depth order (one 8-byte gather per Gaussian, then everything downstream
-// is coalesced) and leaves the per-block pair counts for the scan.  Runs while the host waits for
-// num_rendered.
+// is coalesced) and leaves the pair count of every duplication block (DUP_GAUSS depth ranks) for the
+// scan.  Runs while the host waits for num_rendered.
 __global__ void __launch_bounds__(PRE_THREADS) gather_rects_kernel(const int P, const uint32_t* __restrict__ sorted_ids,
                                                                    const uint2* __restrict__ tile_rects,
                                                                    uint2* __restrict__ sorted_rects,
                                                                    uint32_t* __restrict__ block_sums) {
     __shared__ uint32_t s_warp[PRE_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int i = blockIdx.x * PRE_THREADS + tid;
     uint32_t cnt = 0;
-    if (i < P) {
-        // the tile rect preprocess computed with getRect (GSCuda.cu:237-259; duplicateWithKeys recomputes the
-        // same rect, :445-458).  Gaussians that emit nothing (radii <= 0, :440-443) carry an empty rect.
-        const uint2 rec = __ldg(tile_rects + __ldg(sorted_ids + i));
-        sorted_rects[i] = rec;
-        cnt = (rec.y >> 16) * (rec.y & 0xffffu);
+#pragma unroll
+    for (int c = 0; c < DUP_GPT; ++c) {
+        const int i = blockIdx.x * DUP_GAUSS + c * PRE_THREADS + tid;
+        if (i < P) {
+            // the tile rect preprocess computed with getRect (GSCuda.cu:237-259; duplicateWithKeys recomputes
+            // the same rect, :445-458).  Gaussians that emit nothing (radii <= 0, :440-443) carry an empty rect.
+            const uint2 rec = __ldg(tile_rects + __ldg(sorted_ids + i));
+            sorted_rects[i] = rec;
+            cnt += (rec.y >> 16) * (rec.y & 0xffffu);
+        }
     }
     const uint32_t wsum = __reduce_add_sync(0xffffffffu, cnt);
     if (lane == 0) s_warp[warp] = wsum;
@@ -122,36 +127,58 @@ __global__ void __launch_bounds__(PRE_THREADS) gather_rects_kernel(const int P, 
     }
 }
 
-// Duplication in depth order.  Block b takes the 256 Gaussians at depth ranks 256b .. 256b+255, scans
-// their tile counts and emits every (tile, Gaussian) pair behind the block's scanned offset: rows
-// outer, columns inner (GSCuda.cu:461-474).  The work is pooled: the block's threads walk the pooled
-// output range item by item, so one huge splat does not serialise a thread and the stores are fully
-// coalesced.  The digit histograms of the tile passes are counted here (shared-memory atomics, flushed
-// once per block), so the sort never re-reads the keys.
+// Duplication in depth order.  Block b takes the DUP_GAUSS Gaussians at depth ranks DUP_GAUSS*b ..,
+// (thread t owns ranks 4t..4t+3 of the block), scans their tile counts and emits every (tile, Gaussian)
+// pair behind the block's scanned offset: rows outer, columns inner (GSCuda.cu:461-474).  The work is
+// pooled: outputs are produced in windows of 4*256, thread t producing outputs 4t..4t+3 of the window (one
+// binary search over the pooled counts, then a walk along the rect rows); the window is transposed
+// through shared memory so the stores are fully coalesced and one huge splat cannot serialise a
+// thread.  The digit histograms of the tile passes are counted here (shared-memory atomics, flushed once
+// per block), so the sort never re-reads the keys.
 __global__ void __launch_bounds__(PRE_THREADS) duplicate_sorted_kernel(
     const int P, const int grid_x, const uint32_t* __restrict__ sorted_ids, const uint2* __restrict__ sorted_rects,
     const uint32_t* __restrict__ block_offsets, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
     uint32_t* __restrict__ hist, const int tile_bits) {
-    __shared__ uint32_t s_excl[PRE_THREADS + 1];
+    __shared__ uint32_t s_excl[DUP_GAUSS + 1];
     __shared__ uint32_t s_warp[PRE_THREADS / 32];
-    __shared__ uint32_t s_gid[PRE_THREADS];
-    __shared__ uint32_t s_origin[PRE_THREADS];  // miny << 16 | minx
-    __shared__ uint32_t s_width[PRE_THREADS];
+    __shared__ uint32_t s_gid[DUP_GAUSS];
+    __shared__ uint32_t s_origin[DUP_GAUSS];  // miny << 16 | minx
+    __shared__ uint32_t s_width[DUP_GAUSS];
     __shared__ uint32_t s_hist[4 * 256];
     __shared__ __align__(16) uint32_t s_okey[DUP_ITEMS * PRE_THREADS];
     __shared__ __align__(16) uint32_t s_oval[DUP_ITEMS * PRE_THREADS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int passes = (tile_bits + 7) >> 3;
-    const int i = blockIdx.x * PRE_THREADS + tid;
-    const bool valid = i < P;
-    const uint2 rec = valid ? __ldg(sorted_rects + i) : make_uint2(0u, 0u);
-    const uint32_t cnt = (rec.y >> 16) * (rec.y & 0xffffu);
-    const unsigned any = __ballot_sync(0xffffffffu, cnt != 0);
-    if (__syncthreads_or(any != 0) == 0) return;  // the culled tail of the depth order emits nothing
+    const int i0 = blockIdx.x * DUP_GAUSS + DUP_GPT * tid;
+    // every global load of the block is issued here, before anything waits
+    const uint32_t boff = __ldg(block_offsets + blockIdx.x);
+    uint2 rec[DUP_GPT];
+    uint32_t gid[DUP_GPT];
+    if (i0 + DUP_GPT <= P) {
+        const uint4 r01 = __ldg(reinterpret_cast<const uint4*>(sorted_rects + i0));
+        const uint4 r23 = __ldg(reinterpret_cast<const uint4*>(sorted_rects + i0) + 1);
+        const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(sorted_ids + i0));
+        rec[0] = make_uint2(r01.x, r01.y); rec[1] = make_uint2(r01.z, r01.w);
+        rec[2] = make_uint2(r23.x, r23.y); rec[3] = make_uint2(r23.z, r23.w);
+        gid[0] = g4.x; gid[1] = g4.y; gid[2] = g4.z; gid[3] = g4.w;
+    } else {
+#pragma unroll
+        for (int c = 0; c < DUP_GPT; ++c) {
+            const bool ok = i0 + c < P;
+            rec[c] = ok ? __ldg(sorted_rects + i0 + c) : make_uint2(0u, 0u);
+            gid[c] = ok ? __ldg(sorted_ids + i0 + c) : 0u;
+        }
+    }
     for (int j = tid; j < passes * 256; j += PRE_THREADS) s_hist[j] = 0;
 
-    uint32_t incl = cnt;
+    uint32_t cnt[DUP_GPT], tsum = 0;
+#pragma unroll
+    for (int c = 0; c < DUP_GPT; ++c) {
+        cnt[c] = (rec[c].y >> 16) * (rec[c].y & 0xffffu);
+        tsum += cnt[c];
+    }
+    uint32_t incl = tsum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
@@ -165,20 +192,23 @@ __global__ void __launch_bounds__(PRE_THREADS) duplicate_sorted_kernel(
         if (w < warp) woff += s_warp[w];
         total += s_warp[w];
     }
-    incl += woff;
-    s_excl[tid] = incl - cnt;
-    if (tid == PRE_THREADS - 1) s_excl[PRE_THREADS] = incl;
-    if (cnt > 0) {
-        s_gid[tid] = __ldg(sorted_ids + i);
-        s_origin[tid] = rec.x;
-        s_width[tid] = rec.y & 0xffffu;
+    if (total == 0) return;  // the culled tail of the depth order emits nothing (block-uniform)
+    {
+        uint32_t run = woff + incl - tsum;
+#pragma unroll
+        for (int c = 0; c < DUP_GPT; ++c) {
+            const int q = DUP_GPT * tid + c;
+            s_excl[q] = run;
+            run += cnt[c];
+            s_gid[q] = gid[c];
+            s_origin[q] = rec[c].x;
+            s_width[q] = rec[c].y & 0xffffu;
+        }
+        if (tid == PRE_THREADS - 1) s_excl[DUP_GAUSS] = run;
     }
     __syncthreads();
 
-    const uint32_t boff = block_offsets[blockIdx.x];
     const uint32_t lowmask = (1u << min(8, tile_bits)) - 1u;
-    // Windows of 4*256 outputs: thread t produces outputs 4t..4t+3 of the window (one binary search, then
-    // a walk along the rect rows), the window is transposed through shared memory and stored coalesced.
     for (uint32_t kb = 0; kb < total; kb += DUP_ITEMS * PRE_THREADS) {
         const uint32_t k0 = kb + DUP_ITEMS * tid;
         uint32_t okey[DUP_ITEMS], oval[DUP_ITEMS];
@@ -186,13 +216,13 @@ __global__ void __launch_bounds__(PRE_THREADS) duplicate_sorted_kernel(
         for (int j = 0; j < DUP_ITEMS; ++j) okey[j] = oval[j] = 0;
         if (k0 < total) {
             // largest j with s_excl[j] <= k0
-            int lo = 0, hi = PRE_THREADS - 1;
+            int lo = 0, hi = DUP_GAUSS - 1;
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
+            for (int it = 0; it < 10; ++it) {
                 const int mid = (lo + hi + 1) >> 1;
                 if (s_excl[mid] <= k0) lo = mid; else hi = mid - 1;
             }
-            uint32_t w = s_width[lo], org = s_origin[lo], gid = s_gid[lo], next = s_excl[lo + 1];
+            uint32_t w = s_width[lo], org = s_origin[lo], g = s_gid[lo], next = s_excl[lo + 1];
             const uint32_t t = k0 - s_excl[lo];
             const uint32_t ty = t / w;
             uint32_t tx = t - ty * w;
@@ -204,16 +234,17 @@ __global__ void __launch_bounds__(PRE_THREADS) duplicate_sorted_kernel(
                 if (k < total) {
                     if (k >= next) {  // next Gaussian that emits anything (empty ones have equal offsets)
                         do { ++lo; next = s_excl[lo + 1]; } while (k >= next);
-                        w = s_width[lo]; org = s_origin[lo]; gid = s_gid[lo];
+                        w = s_width[lo]; org = s_origin[lo]; g = s_gid[lo];
                         tx = 0;
                         row_tile = (org >> 16) * (uint32_t)grid_x + (org & 0xffffu);
                     }
                     // key = tile id (GSCuda.cu:466-471: the depth half is re-attached by the last sort pass)
                     const uint32_t tile = row_tile + tx;
-                    okey[j] = tile; oval[j] = gid;
+                    okey[j] = tile; oval[j] = g;
                     if (++tx == w) { tx = 0; row_tile += (uint32_t)grid_x; }
                     atomicAdd(&s_hist[tile & lowmask], 1u);
                     if (passes > 1) {
+                        // a row of tiles shares the higher digits: count runs, not items
                         const uint32_t d = (tile >> 8) & ((1u << min(8, tile_bits - 8)) - 1u);
                         if (d != run_d) {
                             if (run_n) atomicAdd(&s_hist[256 + run_d], run_n);
@@ -241,7 +272,6 @@ __global__ void __launch_bounds__(PRE_THREADS) duplicate_sorted_kernel(
         }
         __syncthreads();
     }
-    __syncthreads();
     for (int j = tid; j < passes * 256; j += PRE_THREADS) {
         const uint32_t c = s_hist[j];
         if (c) atomicAdd(hist + j, c);
@@ -302,10 +332,12 @@ int launch_point_offsets(int P, const uint32_t* tiles_touched, const uint32_t* b
     return e == cudaSuccess ? 1 : -(int)e;
 }
 
+int num_dup_blocks(int P) { return ((P > 0 ? P : 0) + DUP_GAUSS - 1) / DUP_GAUSS; }
+
 int launch_gather_rects(int P, const uint32_t* sorted_ids, const uint32_t* tile_rects, uint32_t* sorted_rects,
                         uint32_t* block_sums, cudaStream_t s) {
     if (P <= 0) return 0;
-    const int blocks = (P + PRE_THREADS - 1) / PRE_THREADS;
+    const int blocks = num_dup_blocks(P);
     gather_rects_kernel<<<blocks, PRE_THREADS, 0, s>>>(P, sorted_ids, reinterpret_cast<const uint2*>(tile_rects),
                                                        reinterpret_cast<uint2*>(sorted_rects), block_sums);
     cudaError_t e = cudaPeekAtLastError();
@@ -317,7 +349,7 @@ int launch_duplicate_sorted(int P, int grid_x, const uint32_t* sorted_ids, const
                             int tile_bits, cudaStream_t s) {
     if (P <= 0) return 0;
     if (tile_bits < 1 || tile_bits > 32) return GSR_ERR_INVALID_ARG;
-    const int blocks = (P + PRE_THREADS - 1) / PRE_THREADS;
+    const int blocks = num_dup_blocks(P);
     duplicate_sorted_kernel<<<blocks, PRE_THREADS, 0, s>>>(P, grid_x, sorted_ids,
                                                            reinterpret_cast<const uint2*>(sorted_rects), block_offsets,
                                                            keys32_out, vals_out, hist, tile_bits);

@@ -296,7 +296,8 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         // tile rects into depth order + scan of the per-block pair counts (same total, other order)
         GSR_STAGE(launch_gather_rects(P, geom.depth_sort_ids[1], geom.tile_rects, geom.sorted_rects,
                                       geom.sorted_block_sums, s));
-        GSR_STAGE(launch_scan_block_sums(geom.sorted_block_sums, nb, geom.sorted_block_sums + nb, nullptr, s));
+        const int ndb = num_dup_blocks(P);
+        GSR_STAGE(launch_scan_block_sums(geom.sorted_block_sums, ndb, geom.sorted_block_sums + ndb, nullptr, s));
         GSR_STAGE(launch_point_offsets(P, geom.tiles_touched, geom.block_sums, geom.point_offsets, s));
         tm.mark();  // 3
         // the one host round trip: num_rendered decides the binning allocation (GSCuda.cu:772,782)

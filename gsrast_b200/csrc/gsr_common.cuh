@@ -70,7 +70,9 @@ int launch_scan_block_sums(uint32_t* block_sums, int num_blocks, uint32_t* total
 // already hold the exclusive block offsets.
 int launch_point_offsets(int P, const uint32_t* tiles_touched, const uint32_t* block_sums, uint32_t* point_offsets,
                          cudaStream_t s);
-// sorted_rects[i] = tile_rects[sorted_ids[i]] and block_sums[b] = pairs emitted by depth ranks 256b..256b+255.
+// Duplication blocks take num_dup_blocks(P) groups of consecutive depth ranks.
+int num_dup_blocks(int P);
+// sorted_rects[i] = tile_rects[sorted_ids[i]] and block_sums[b] = pairs emitted by the depth ranks of block b.
 int launch_gather_rects(int P, const uint32_t* sorted_ids, const uint32_t* tile_rects, uint32_t* sorted_rects,
                         uint32_t* block_sums, cudaStream_t s);
 // Emits the (tile, Gaussian) pairs of the Gaussians taken in depth order: 32-bit tile keys + Gaussian

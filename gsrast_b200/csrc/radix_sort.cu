@@ -43,7 +43,13 @@ constexpr int SORT_THREADS = 256;  // == RADIX: thread d owns digit d in the sca
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 // Items per thread: 16 (4096-pair tiles) for the big pair-level passes, 8 for the Gaussian-level
 // depth passes, whose few hundred tiles would otherwise not fill the machine twice.
-constexpr int ITEMS_LARGE = 16;
+#ifndef GSR_ITEMS_LARGE
+#define GSR_ITEMS_LARGE 16
+#endif
+#ifndef GSR_MINB_LARGE
+#define GSR_MINB_LARGE 4
+#endif
+constexpr int ITEMS_LARGE = GSR_ITEMS_LARGE;
 constexpr int ITEMS_SMALL = 8;
 constexpr int MAX_PASSES = 8;
 #ifndef GSR_LOOKBACK_W
@@ -535,15 +541,15 @@ int launch_sort32(const Sort32Plan& p, cudaStream_t s, cudaEvent_t* events) {
             if (p.expand_low) {
                 a.expand_low = p.expand_low; a.keys_out64 = p.keys_out64;
                 rc = items == ITEMS_SMALL ? launch_pass<uint32_t, true, 4, ITEMS_SMALL>(a, s)
-                                          : launch_pass<uint32_t, true, 3, ITEMS_LARGE>(a, s);
+                                          : launch_pass<uint32_t, true, GSR_MINB_LARGE - 1, ITEMS_LARGE>(a, s);
             } else {
                 rc = items == ITEMS_SMALL ? launch_pass<uint32_t, false, 6, ITEMS_SMALL>(a, s)
-                                          : launch_pass<uint32_t, false, 4, ITEMS_LARGE>(a, s);
+                                          : launch_pass<uint32_t, false, GSR_MINB_LARGE, ITEMS_LARGE>(a, s);
             }
         } else {
             a.keys_out = p.kbuf[ps & 1]; a.vals_out = p.vbuf[ps & 1];
             rc = items == ITEMS_SMALL ? launch_pass<uint32_t, false, 6, ITEMS_SMALL>(a, s)
-                                      : launch_pass<uint32_t, false, 4, ITEMS_LARGE>(a, s);
+                                      : launch_pass<uint32_t, false, GSR_MINB_LARGE, ITEMS_LARGE>(a, s);
             kin = p.kbuf[ps & 1]; vin = p.vbuf[ps & 1];
         }
         if (rc < 0) return rc;

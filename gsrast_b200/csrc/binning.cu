@@ -18,11 +18,14 @@ namespace gsr {
 namespace {
 
 constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 16;
 constexpr int DUP_ITEMS = 4;  // consecutive outputs per thread and window in the duplication kernel
 constexpr int DUP_GPT = 4;    // Gaussians (consecutive depth ranks) per thread of a duplication block
 constexpr int DUP_GAUSS = DUP_GPT * PRE_THREADS;
 
 // Exclusive scan of block_sums[n] in place; total -> *total_dev and *total_host (mapped).
+// One CTA; every thread owns SCAN_ITEMS consecutive entries (vector loads), so up to 16K entries
+// (4.2 M Gaussians) take a single round of one warp scan + one cross-warp scan.
 __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(uint32_t* __restrict__ block_sums, int n,
                                                                        uint32_t* __restrict__ total_dev,
                                                                        volatile uint32_t* total_host) {
@@ -30,11 +33,27 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(uint32_t*
     __shared__ uint32_t s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_carry = 0;
+    gsr_pdl_wait();
+    gsr_pdl_launch_dependents();
     __syncthreads();
-    for (int base = 0; base < n; base += SCAN_THREADS) {
-        const int i = base + tid;
-        const uint32_t v = (i < n) ? block_sums[i] : 0u;
-        uint32_t incl = v;
+    constexpr int CHUNK = SCAN_THREADS * SCAN_ITEMS;
+    for (int base = 0; base < n; base += CHUNK) {
+        const int i0 = base + tid * SCAN_ITEMS;
+        uint32_t v[SCAN_ITEMS];
+        if (i0 + SCAN_ITEMS <= n) {
+#pragma unroll
+            for (int q = 0; q < SCAN_ITEMS / 4; ++q) {
+                const uint4 x = reinterpret_cast<const uint4*>(block_sums + i0)[q];
+                v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < SCAN_ITEMS; ++j) v[j] = (i0 + j < n) ? block_sums[i0 + j] : 0u;
+        }
+        uint32_t tsum = 0;
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) tsum += v[j];
+        uint32_t incl = tsum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
@@ -54,10 +73,24 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(uint32_t*
         }
         __syncthreads();
         const uint32_t carry = s_carry;
-        const uint32_t excl = carry + s_warp[warp] + incl - v;
-        if (i < n) block_sums[i] = excl;
+        uint32_t run = carry + s_warp[warp] + incl - tsum;
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) {
+            const uint32_t x = v[j];
+            v[j] = run;
+            run += x;
+        }
+        if (i0 + SCAN_ITEMS <= n) {
+#pragma unroll
+            for (int q = 0; q < SCAN_ITEMS / 4; ++q)
+                reinterpret_cast<uint4*>(block_sums + i0)[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < SCAN_ITEMS; ++j)
+                if (i0 + j < n) block_sums[i0 + j] = v[j];
+        }
         __syncthreads();
-        if (tid == SCAN_THREADS - 1) s_carry = excl + v;
+        if (tid == SCAN_THREADS - 1) s_carry = run;
         __syncthreads();
     }
     if (tid == 0) {
@@ -70,40 +103,27 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(uint32_t*
     }
 }
 
-// Inclusive scan of tiles_touched in index order — the array cub::DeviceScan::InclusiveSum leaves in
-// pointOffsets (GSCuda.cu:771), which the Inspector reads (Inspector.cpp:174-188).  The pipeline itself
-// consumes the scan in depth order (duplicate_sorted_kernel), so this is materialised on the side.
-__global__ void __launch_bounds__(PRE_THREADS) point_offsets_kernel(const int P, const uint32_t* __restrict__ tiles_touched,
-                                                                    const uint32_t* __restrict__ block_offsets,
-                                                                    uint32_t* __restrict__ point_offsets) {
-    __shared__ uint32_t s_warp[PRE_THREADS / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int idx = blockIdx.x * PRE_THREADS + tid;
-    const uint32_t cnt = idx < P ? tiles_touched[idx] : 0u;
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    uint32_t woff = 0;
-#pragma unroll
-    for (int w = 0; w < PRE_THREADS / 32; ++w)
-        if (w < warp) woff += s_warp[w];
-    if (idx < P) point_offsets[idx] = block_offsets[blockIdx.x] + woff + incl;
-}
-
-// Gathers the tile rects into depth order (one 8-byte gather per Gaussian, then everything downstream
-// is coalesced) and leaves the pair count of every duplication block (DUP_GAUSS depth ranks) for the
-// scan.  Runs while the host waits for num_rendered.
+// Two independent jobs of the window in which the host waits for num_rendered, in one launch:
+//  (a) gather the tile rects into depth order (one 8-byte gather per Gaussian, then everything
+//      downstream is coalesced) and leave the pair count of every duplication block (DUP_GAUSS depth
+//      ranks) for the scan;
+//  (b) materialise point_offsets = inclusive scan of tiles_touched in INDEX order — the array
+//      cub::DeviceScan::InclusiveSum leaves in pointOffsets (GSCuda.cu:771), which the Inspector reads
+//      (Inspector.cpp:174-188).  The pipeline itself consumes the scan in depth order, so this is on
+//      the side.  `block_offsets` are the exclusive offsets of preprocess' 256-Gaussian blocks.
 __global__ void __launch_bounds__(PRE_THREADS) gather_rects_kernel(const int P, const uint32_t* __restrict__ sorted_ids,
                                                                    const uint2* __restrict__ tile_rects,
                                                                    uint2* __restrict__ sorted_rects,
-                                                                   uint32_t* __restrict__ block_sums) {
+                                                                   uint32_t* __restrict__ block_sums,
+                                                                   const uint32_t* __restrict__ tiles_touched,
+                                                                   const uint32_t* __restrict__ block_offsets,
+                                                                   uint32_t* __restrict__ point_offsets) {
     __shared__ uint32_t s_warp[PRE_THREADS / 32];
+    __shared__ uint32_t s_pw[PRE_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    gsr_pdl_wait();
+    gsr_pdl_launch_dependents();
+    // (a)
     uint32_t cnt = 0;
 #pragma unroll
     for (int c = 0; c < DUP_GPT; ++c) {
@@ -116,9 +136,44 @@ __global__ void __launch_bounds__(PRE_THREADS) gather_rects_kernel(const int P, 
             cnt += (rec.y >> 16) * (rec.y & 0xffffu);
         }
     }
+    // (b) thread t owns indices 4t..4t+3 of the block's 1024; 64 threads = one preprocess block
+    const int i0 = blockIdx.x * DUP_GAUSS + 4 * tid;
+    uint32_t tt[4] = {0u, 0u, 0u, 0u};
+    if (i0 + 4 <= P) {
+        const uint4 x = __ldg(reinterpret_cast<const uint4*>(tiles_touched + i0));
+        tt[0] = x.x; tt[1] = x.y; tt[2] = x.z; tt[3] = x.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (i0 + j < P) tt[j] = __ldg(tiles_touched + i0 + j);
+    }
+    const uint32_t tsum = tt[0] + tt[1] + tt[2] + tt[3];
+    uint32_t incl = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_pw[warp] = incl;
     const uint32_t wsum = __reduce_add_sync(0xffffffffu, cnt);
     if (lane == 0) s_warp[warp] = wsum;
     __syncthreads();
+    if (i0 < P) {
+        uint32_t run = __ldg(block_offsets + (i0 / PRE_THREADS)) + ((warp & 1) ? s_pw[warp - 1] : 0u) + incl - tsum;
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            run += tt[j];
+            o[j] = run;
+        }
+        if (i0 + 4 <= P) {
+            reinterpret_cast<uint4*>(point_offsets + i0)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (i0 + j < P) point_offsets[i0 + j] = o[j];
+        }
+    }
     if (tid == 0) {
         uint32_t t = 0;
 #pragma unroll
@@ -151,6 +206,8 @@ __global__ void __launch_bounds__(PRE_THREADS) duplicate_sorted_kernel(
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int passes = (tile_bits + 7) >> 3;
     const int i0 = blockIdx.x * DUP_GAUSS + DUP_GPT * tid;
+    gsr_pdl_wait();
+    gsr_pdl_launch_dependents();
     // every global load of the block is issued here, before anything waits
     const uint32_t boff = __ldg(block_offsets + blockIdx.x);
     uint2 rec[DUP_GPT];
@@ -284,6 +341,8 @@ template <bool COMPAT>
 __global__ void __launch_bounds__(256) identify_ranges_kernel(const size_t n, const uint64_t* __restrict__ keys,
                                                               uint2* __restrict__ ranges) {
     const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    gsr_pdl_wait();
+    gsr_pdl_launch_dependents();
     if (i0 >= n) return;
     uint64_t k[4];
     if (i0 + 3 < n) {
@@ -318,29 +377,21 @@ __global__ void __launch_bounds__(256) identify_ranges_kernel(const size_t n, co
 
 int launch_scan_block_sums(uint32_t* block_sums, int num_blocks, uint32_t* total_dev, uint32_t* total_host_mapped,
                            cudaStream_t s) {
-    scan_block_sums_kernel<<<1, SCAN_THREADS, 0, s>>>(block_sums, num_blocks, total_dev, total_host_mapped);
-    cudaError_t e = cudaPeekAtLastError();
-    return e == cudaSuccess ? 1 : -(int)e;
-}
-
-int launch_point_offsets(int P, const uint32_t* tiles_touched, const uint32_t* block_sums, uint32_t* point_offsets,
-                         cudaStream_t s) {
-    if (P <= 0) return 0;
-    const int blocks = (P + PRE_THREADS - 1) / PRE_THREADS;
-    point_offsets_kernel<<<blocks, PRE_THREADS, 0, s>>>(P, tiles_touched, block_sums, point_offsets);
-    cudaError_t e = cudaPeekAtLastError();
+    cudaError_t e = launch_pdl(scan_block_sums_kernel, dim3(1), dim3(SCAN_THREADS), 0, s, block_sums, num_blocks, total_dev,
+                               (volatile uint32_t*)total_host_mapped);
     return e == cudaSuccess ? 1 : -(int)e;
 }
 
 int num_dup_blocks(int P) { return ((P > 0 ? P : 0) + DUP_GAUSS - 1) / DUP_GAUSS; }
 
 int launch_gather_rects(int P, const uint32_t* sorted_ids, const uint32_t* tile_rects, uint32_t* sorted_rects,
-                        uint32_t* block_sums, cudaStream_t s) {
+                        uint32_t* block_sums, const uint32_t* tiles_touched, const uint32_t* block_offsets,
+                        uint32_t* point_offsets, cudaStream_t s) {
     if (P <= 0) return 0;
     const int blocks = num_dup_blocks(P);
-    gather_rects_kernel<<<blocks, PRE_THREADS, 0, s>>>(P, sorted_ids, reinterpret_cast<const uint2*>(tile_rects),
-                                                       reinterpret_cast<uint2*>(sorted_rects), block_sums);
-    cudaError_t e = cudaPeekAtLastError();
+    cudaError_t e = launch_pdl(gather_rects_kernel, dim3(blocks), dim3(PRE_THREADS), 0, s, P, sorted_ids,
+                               reinterpret_cast<const uint2*>(tile_rects), reinterpret_cast<uint2*>(sorted_rects),
+                               block_sums, tiles_touched, block_offsets, point_offsets);
     return e == cudaSuccess ? 1 : -(int)e;
 }
 
@@ -358,16 +409,16 @@ int launch_duplicate_sorted(int P, int grid_x, const uint32_t* sorted_ids, const
 }
 
 int launch_identify_ranges(const uint64_t* keys, size_t n, uint32_t* ranges, int num_tiles, bool compat,
-                           cudaStream_t s) {
-    cudaError_t e = cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)num_tiles, s);
+                           cudaStream_t s, bool zero_first) {
+    cudaError_t e = cudaSuccess;
+    if (zero_first) e = cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)num_tiles, s);
     if (e != cudaSuccess) return -(int)e;
     if (n == 0) return 0;
     const unsigned blocks = (unsigned)((n + 1023) / 1024);
     if (compat)
-        identify_ranges_kernel<true><<<blocks, 256, 0, s>>>(n, keys, reinterpret_cast<uint2*>(ranges));
+        e = launch_pdl(identify_ranges_kernel<true>, dim3(blocks), dim3(256), 0, s, n, keys, reinterpret_cast<uint2*>(ranges));
     else
-        identify_ranges_kernel<false><<<blocks, 256, 0, s>>>(n, keys, reinterpret_cast<uint2*>(ranges));
-    e = cudaPeekAtLastError();
+        e = launch_pdl(identify_ranges_kernel<false>, dim3(blocks), dim3(256), 0, s, n, keys, reinterpret_cast<uint2*>(ranges));
     return e == cudaSuccess ? 1 : -(int)e;
 }
 

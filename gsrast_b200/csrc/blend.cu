@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_simple_kernel(const Blend
     const bool inside = pix_x < p.W && pix_y < p.H;
     const float pixf_x = (float)pix_x, pixf_y = (float)pix_y;
 
+    gsr_pdl_wait();
     const uint2 range = reinterpret_cast<const uint2*>(p.ranges)[tile];
     const int total = (int)(range.y - range.x);
     const int rounds = (total + BATCH - 1) / BATCH;
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_culled_kernel(const Blend
     const uint32_t lane_lt = (1u << lane) - 1u;
     unsigned char* my_list = s_list[warp];
 
+    gsr_pdl_wait();
     const uint2 range = reinterpret_cast<const uint2*>(p.ranges)[tile];
     const int total = (int)(range.y - range.x);
     const int rounds = (total + BATCH - 1) / BATCH;
@@ -274,11 +276,11 @@ __global__ void fill_background_kernel(int n, const float* __restrict__ backgrou
 int launch_blend(const BlendParams& p, bool simple, cudaStream_t s) {
     const int tiles = p.grid_x * p.grid_y;
     if (tiles <= 0) return 0;
+    cudaError_t e;
     if (simple)
-        blend_simple_kernel<<<tiles, BLEND_THREADS, 0, s>>>(p);
+        e = launch_pdl(blend_simple_kernel, dim3(tiles), dim3(BLEND_THREADS), 0, s, p);
     else
-        blend_culled_kernel<<<tiles, BLEND_THREADS, 0, s>>>(p);
-    cudaError_t e = cudaPeekAtLastError();
+        e = launch_pdl(blend_culled_kernel, dim3(tiles), dim3(BLEND_THREADS), 0, s, p);
     return e == cudaSuccess ? 1 : -(int)e;
 }
 

@@ -275,6 +275,12 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         pp.means2D = geom.means2D; pp.cov3D = geom.cov3D; pp.conic_opacity = geom.conic_opacity;
         pp.rgb = geom.rgb; pp.tiles_touched = geom.tiles_touched; pp.block_sums = geom.block_sums;
         pp.depth_keys = geom.depth_keys; pp.tile_rects = geom.tile_rects;
+        // all clears of the frame up front, so the kernels behind them form uninterrupted dependent-launch chains
+        if (!sort32_prepare(geom.depth_sort_space, (size_t)P, 32, s)) GSR_FAIL(-(int)cudaGetLastError());
+        {
+            cudaError_t ez = cudaMemsetAsync(img.ranges, 0, sizeof(uint32_t) * 2 * (size_t)tiles, s);
+            if (ez != cudaSuccess) GSR_FAIL(-(int)ez);
+        }
         GSR_STAGE(launch_preprocess(pp, compat, s));
         tm.mark();  // 1
         const int nb = num_pre_blocks(P);
@@ -283,7 +289,6 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         if (e != cudaSuccess) GSR_FAIL(-(int)e);
         tm.mark();  // 2
         // ---- depth half of the sort: P records, queued before the host waits --------------------
-        if (!sort32_prepare(geom.depth_sort_space, (size_t)P, 32, s)) GSR_FAIL(-(int)cudaGetLastError());
         Sort32Plan dp;
         memset(&dp, 0, sizeof(dp));
         dp.n = (size_t)P; dp.end_bit = 32;
@@ -295,10 +300,9 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         GSR_STAGE(launch_sort32(dp, s, sort_timed ? sort_ev : nullptr));
         // tile rects into depth order + scan of the per-block pair counts (same total, other order)
         GSR_STAGE(launch_gather_rects(P, geom.depth_sort_ids[1], geom.tile_rects, geom.sorted_rects,
-                                      geom.sorted_block_sums, s));
+                                      geom.sorted_block_sums, geom.tiles_touched, geom.block_sums, geom.point_offsets, s));
         const int ndb = num_dup_blocks(P);
         GSR_STAGE(launch_scan_block_sums(geom.sorted_block_sums, ndb, geom.sorted_block_sums + ndb, nullptr, s));
-        GSR_STAGE(launch_point_offsets(P, geom.tiles_touched, geom.block_sums, geom.point_offsets, s));
         tm.mark();  // 3
         // the one host round trip: num_rendered decides the binning allocation (GSCuda.cu:772,782)
         e = cudaEventSynchronize(slot.landed);
@@ -356,7 +360,7 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         GSR_STAGE(launch_sort32(tp, s, sort_timed ? sort_ev + 6 : nullptr));
     }
     tm.mark();  // 5
-    GSR_STAGE(launch_identify_ranges(bin.point_list_keys, R, img.ranges, tiles, compat, s));
+    GSR_STAGE(launch_identify_ranges(bin.point_list_keys, R, img.ranges, tiles, compat, s, /*zero_first=*/false));
     tm.mark();  // 6
 
     BlendParams bp;

@@ -86,6 +86,8 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(const Preproces
     const int idx = base + tid;
     const int nvalid = min(PRE_THREADS, p.P - base);
     const bool valid = tid < nvalid;
+    gsr_pdl_wait();
+    gsr_pdl_launch_dependents();  // the scan behind this kernel may take freed SM slots early (it waits)
 
     // ---- stage camera + float3 streams -------------------------------------------------
     if (tid < 16) s_cam[tid] = __ldg(p.viewmatrix + tid);
@@ -173,6 +175,14 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(const Preproces
             tvx = fadd(fadd(fmul(v[0], px), fmul(v[4], py)), fadd(fmul(v[8], pz), fmul(v[12], 1.0f)));
             tvy = fadd(fadd(fmul(v[1], px), fmul(v[5], py)), fadd(fmul(v[9], pz), fmul(v[13], 1.0f)));
             tvz = fadd(fadd(fmul(v[2], px), fmul(v[6], py)), fadd(fmul(v[10], pz), fmul(v[14], 1.0f)));
+        }
+
+        // The SH block of a Gaussian that passed the frustum test is needed ~200 instructions from now (after
+        // the covariance math and the warp compaction): start pulling its two 128-byte lines into L2.
+        if (!COMPAT && alive && p.colors_precomp == nullptr) {
+            const char* shp = reinterpret_cast<const char*>(p.shs + (size_t)idx * p.M * 3);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(shp));
+            if (p.M * 12 > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(shp + 128));
         }
 
         float cov00 = 0.f, cov01 = 0.f, cov11 = 0.f;

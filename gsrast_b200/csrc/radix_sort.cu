@@ -61,6 +61,8 @@ constexpr uint32_t FLAG_AGG = 1u << 30;
 constexpr uint32_t FLAG_INC = 2u << 30;
 constexpr uint32_t FLAG_MASK = 3u << 30;
 constexpr uint32_t VAL_MASK = ~FLAG_MASK;
+constexpr int GROUP_SHIFT = 4;  // look-back groups of 16 tiles (16 * 6144 items < 2^24: sum and arrivals share a word)
+constexpr int GROUP_TILES = 1 << GROUP_SHIFT;
 
 constexpr int HIST_THREADS = 256;
 
@@ -90,6 +92,8 @@ __global__ void __launch_bounds__(HIST_THREADS) histogram_kernel(const KeyT* __r
     __shared__ uint32_t s_hist[PASSES * RADIX];
     const int tid = threadIdx.x;
     for (int i = tid; i < PASSES * RADIX; i += HIST_THREADS) s_hist[i] = 0;
+    gsr_pdl_wait();
+    gsr_pdl_launch_dependents();
     __syncthreads();
 
     constexpr int PER_THREAD = 8;
@@ -121,29 +125,6 @@ __global__ void __launch_bounds__(HIST_THREADS) histogram_kernel(const KeyT* __r
     }
 }
 
-// hist[pass][d] -> exclusive prefix over d, in place.  One CTA, one pass per iteration.
-__global__ void __launch_bounds__(RADIX) scan_histograms_kernel(uint32_t* __restrict__ hist, const int passes) {
-    __shared__ uint32_t s_w[RADIX / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int ps = 0; ps < passes; ++ps) {
-        const uint32_t v = hist[ps * RADIX + tid];
-        uint32_t incl = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        if (lane == 31) s_w[warp] = incl;
-        __syncthreads();
-        uint32_t off = 0;
-#pragma unroll
-        for (int w = 0; w < RADIX / 32; ++w)
-            if (w < warp) off += s_w[w];
-        hist[ps * RADIX + tid] = off + incl - v;
-        __syncthreads();
-    }
-}
-
 // Status words carry flag and count in ONE 32-bit word, so relaxed gpu-scope accesses suffice.
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
     uint32_t v;
@@ -152,6 +133,9 @@ __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
 }
 __device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_relaxed_u32(uint32_t* p, uint32_t v) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // ---- one digit pass ------------------------------------------------------------------------
@@ -162,8 +146,9 @@ struct PassArgs {
     uint32_t* vals_out;
     size_t n;
     int shift, nbits;
-    const uint32_t* digit_offsets;  // [RADIX] exclusive offsets of this pass
+    const uint32_t* digit_counts;   // [RADIX] global digit histogram of this pass (every CTA scans it itself)
     uint32_t* status;               // [num_tiles][RADIX], zero-initialised
+    uint32_t* gstat;                // [ceil(num_tiles/16)][RADIX], zero-initialised: arrivals << 24 | sum of counts
     uint32_t* ticket;
     uint32_t* error_flag;
     // last tile-digit pass of the forward path: key64 = key32 << 32 | expand_low[value]
@@ -175,7 +160,7 @@ struct PassArgs {
 // [SORT_WARPS][RADIX] | per-warp match masks [SORT_WARPS][RADIX] | global bases [RADIX] | misc[16].
 template <typename KeyT, int SORT_ITEMS>
 constexpr size_t onesweep_smem() {
-    return (size_t)SORT_THREADS * SORT_ITEMS * (sizeof(KeyT) + 4) + (size_t)(2 * SORT_WARPS * RADIX + RADIX + 16) * 4;
+    return (size_t)SORT_THREADS * SORT_ITEMS * (sizeof(KeyT) + 4) + (size_t)(2 * SORT_WARPS * RADIX + RADIX + 32) * 4;
 }
 
 template <typename KeyT, bool EXPAND, bool FULL, int SORT_ITEMS>
@@ -229,28 +214,36 @@ __device__ __forceinline__ void onesweep_tile(const PassArgs& a, const uint32_t 
     for (int w = 0; w < SORT_WARPS; ++w) bins += s_whist[w * RADIX + tid];
     uint32_t* my_status = a.status + (size_t)tile * RADIX + tid;
     st_relaxed_u32(my_status, (tile == 0 ? FLAG_INC : FLAG_AGG) | bins);
-    // first look-back window: these loads fly while the block ranks
+    // group aggregate: lets a look-back skip 16 tiles with one word once all of them have arrived
+    red_add_relaxed_u32(a.gstat + (size_t)(tile >> GROUP_SHIFT) * RADIX + tid, (1u << 24) | bins);
+    // first look-back window (own group only): these loads fly while the block ranks
+    const int64_t gstart = (int64_t)(tile >> GROUP_SHIFT) << GROUP_SHIFT;
     uint32_t look[LOOKBACK_W];
 #pragma unroll
     for (int w = 0; w < LOOKBACK_W; ++w) {
         const int64_t tw = (int64_t)tile - 1 - w;
-        look[w] = (tw >= 0) ? ld_relaxed_u32(a.status + (size_t)tw * RADIX + tid) : FLAG_INC;
+        look[w] = (tw >= gstart) ? ld_relaxed_u32(a.status + (size_t)tw * RADIX + tid) : FLAG_AGG;
     }
-    uint32_t block_off;
+    // exclusive scans over the digits: of the tile's counts, and of the global histogram (start of every
+    // digit's output range) — two values through the same shuffles
+    uint32_t block_off, digit_off;
     {
-        uint32_t incl = bins;
+        const uint32_t gcnt = a.digit_counts[tid];
+        uint32_t incl = bins, gincl = gcnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            const uint32_t g = __shfl_up_sync(0xffffffffu, gincl, d);
+            if (lane >= d) { incl += t; gincl += g; }
         }
-        if (lane == 31) s_misc[1 + warp] = incl;
+        if (lane == 31) { s_misc[1 + warp] = incl; s_misc[1 + SORT_WARPS + warp] = gincl; }
         __syncthreads();
-        uint32_t off = 0;
+        uint32_t off = 0, goff = 0;
 #pragma unroll
         for (int w = 0; w < SORT_WARPS; ++w)
-            if (w < warp) off += s_misc[1 + w];
+            if (w < warp) { off += s_misc[1 + w]; goff += s_misc[1 + SORT_WARPS + w]; }
         block_off = off + incl - bins;
+        digit_off = goff + gincl - gcnt;
     }
     {
         uint32_t run = block_off;
@@ -291,17 +284,20 @@ __device__ __forceinline__ void onesweep_tile(const PassArgs& a, const uint32_t 
         __syncwarp();
     }
 
-    // 4. decoupled look-back for digit `tid`, LOOKBACK_W predecessor words per round trip
+    // 4. decoupled look-back for digit `tid`.  Phase 1 walks the earlier tiles of the own group of 16
+    //    (individual status words, LOOKBACK_W per round trip); phase 2 walks whole groups, 4 per round
+    //    trip: a group contributes either the inclusive prefix of its last tile (then the walk ends) or,
+    //    once all 16 tiles have arrived, its aggregate.
     {
         uint32_t excl = 0;
         if (tile != 0) {
-            int64_t t = (int64_t)tile - 1;
             bool done = false;
             uint32_t spins = 0;
-            while (!done) {
+            int64_t t = (int64_t)tile - 1;
+            while (!done && t >= gstart) {
 #pragma unroll
                 for (int w = 0; w < LOOKBACK_W; ++w) {
-                    if (done) break;
+                    if (done || t - w < gstart) break;
                     uint32_t v = look[w];
                     while ((v & FLAG_MASK) == 0) {  // predecessor has not published yet
                         if (++spins > (1u << 22)) {  // watchdog: never expected to trip
@@ -315,17 +311,56 @@ __device__ __forceinline__ void onesweep_tile(const PassArgs& a, const uint32_t 
                     excl += v & VAL_MASK;
                     if ((v & FLAG_MASK) == FLAG_INC) done = true;  // tile 0 always publishes FLAG_INC
                 }
-                if (!done) {
-                    t -= LOOKBACK_W;
+                t -= LOOKBACK_W;
+                if (!done && t >= gstart) {
 #pragma unroll
                     for (int w = 0; w < LOOKBACK_W; ++w)
-                        look[w] = (t - w >= 0) ? ld_relaxed_u32(a.status + (size_t)(t - w) * RADIX + tid) : FLAG_INC;
+                        look[w] = (t - w >= gstart) ? ld_relaxed_u32(a.status + (size_t)(t - w) * RADIX + tid) : FLAG_AGG;
                 }
+            }
+            int64_t gi = (int64_t)(tile >> GROUP_SHIFT) - 1;
+            while (!done && gi >= 0) {
+                uint32_t li[4], gs[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int64_t gq = gi - q;
+                    li[q] = gs[q] = 0;
+                    if (gq >= 0) {
+                        li[q] = ld_relaxed_u32(a.status + (size_t)((gq << GROUP_SHIFT) + GROUP_TILES - 1) * RADIX + tid);
+                        gs[q] = ld_relaxed_u32(a.gstat + (size_t)gq * RADIX + tid);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int64_t gq = gi - q;
+                    if (done || gq < 0) break;
+                    uint32_t l = li[q], g = gs[q];
+                    while (true) {
+                        if ((l & FLAG_MASK) == FLAG_INC) {
+                            excl += l & VAL_MASK;
+                            done = true;
+                            break;
+                        }
+                        if ((g >> 24) == GROUP_TILES) {
+                            excl += g & 0xffffffu;
+                            break;
+                        }
+                        if (++spins > (1u << 22)) {
+                            atomicExch(a.error_flag, 1u);
+                            done = true;
+                            break;
+                        }
+                        __nanosleep(32);
+                        l = ld_relaxed_u32(a.status + (size_t)((gq << GROUP_SHIFT) + GROUP_TILES - 1) * RADIX + tid);
+                        g = ld_relaxed_u32(a.gstat + (size_t)gq * RADIX + tid);
+                    }
+                }
+                gi -= 4;
             }
             st_relaxed_u32(my_status, FLAG_INC | ((excl + bins) & VAL_MASK));
         }
         // global index of staged item j of digit d:  s_global[d] + j
-        s_global[tid] = a.digit_offsets[tid] + excl - block_off;
+        s_global[tid] = digit_off + excl - block_off;
     }
     __syncthreads();
 
@@ -371,8 +406,12 @@ __global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) onesweep_kernel(cons
     uint32_t* s_misc = s_whist + 2 * SORT_WARPS * RADIX + RADIX;
     const int tid = threadIdx.x;
     // tiles are handed out in order of execution, so a tile only ever waits for tiles that started
+    // (the ticket word and the look-back state were zeroed before the previous kernel of the stream started,
+    // so the ticket and the shared-memory setup may overlap that kernel's tail)
     if (tid == 0) s_misc[0] = atomicAdd(a.ticket, 1u);
     for (int i = tid; i < 2 * SORT_WARPS * RADIX; i += SORT_THREADS) s_whist[i] = 0;  // counters + masks
+    gsr_pdl_wait();
+    gsr_pdl_launch_dependents();
     __syncthreads();
     const uint32_t tile = s_misc[0];
     const size_t tile_base = (size_t)tile * SORT_TILE;
@@ -386,11 +425,14 @@ __global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) onesweep_kernel(cons
 size_t num_sort_tiles(size_t n, int items) { return (n + (size_t)SORT_THREADS * items - 1) / ((size_t)SORT_THREADS * items); }
 
 struct TempLayout {
-    uint32_t* hist;     // [MAX_PASSES][RADIX]  global digit histograms -> exclusive offsets
+    uint32_t* hist;     // [MAX_PASSES][RADIX]  global digit histograms (raw counts)
     uint32_t* tickets;  // [MAX_PASSES] tile tickets, + [MAX_PASSES] error flag
     uint32_t* status;   // [passes][num_tiles][RADIX]
+    uint32_t* gstat;    // [passes][num_groups][RADIX]
     size_t zero_bytes;
 };
+
+size_t num_groups(size_t tiles) { return (tiles + GROUP_TILES - 1) >> GROUP_SHIFT; }
 
 TempLayout carve_temp(char* temp, size_t n, int passes, int items) {
     TempLayout L;
@@ -400,8 +442,10 @@ TempLayout carve_temp(char* temp, size_t n, int passes, int items) {
     L.tickets = reinterpret_cast<uint32_t*>(t);
     t += align_up((size_t)MAX_PASSES * 2 * 4, 128);
     L.status = reinterpret_cast<uint32_t*>(t);
-    L.zero_bytes = (size_t)(reinterpret_cast<char*>(L.status) - reinterpret_cast<char*>(L.hist)) +
-                   (size_t)passes * num_sort_tiles(n, items) * RADIX * 4;
+    const size_t tiles = num_sort_tiles(n, items);
+    L.gstat = L.status + (size_t)passes * tiles * RADIX;
+    L.zero_bytes = (size_t)(reinterpret_cast<char*>(L.gstat) - reinterpret_cast<char*>(L.hist)) +
+                   (size_t)passes * num_groups(tiles) * RADIX * 4;
     return L;
 }
 
@@ -411,8 +455,8 @@ int launch_histogram(const KeyT* keys, size_t n, int end_bit, int passes, uint32
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t per_block = (size_t)HIST_THREADS * 8;
-    const unsigned hblocks = (unsigned)std::min<size_t>((n + per_block - 1) / per_block, (size_t)sms * 8);
-#define GSR_HIST(PS) histogram_kernel<KeyT, PS><<<hblocks, HIST_THREADS, 0, s>>>(keys, n, end_bit, hist)
+    const unsigned hblocks = (unsigned)std::min<size_t>((n + per_block - 1) / per_block, (size_t)sms * 4);
+#define GSR_HIST(PS) launch_pdl(histogram_kernel<KeyT, PS>, dim3(hblocks), dim3(HIST_THREADS), 0, s, keys, n, end_bit, hist)
     switch (passes) {
         case 1: GSR_HIST(1); break;
         case 2: GSR_HIST(2); break;
@@ -433,7 +477,8 @@ int launch_pass(const PassArgs& a, cudaStream_t s) {
     // per-device attribute; cheap enough to set on every call (one process may drive several GPUs)
     GSR_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS, ITEMS>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS, ITEMS><<<(unsigned)num_sort_tiles(a.n, ITEMS), SORT_THREADS, smem, s>>>(a);
+    GSR_CUDA_TRY(launch_pdl(onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS, ITEMS>, dim3((unsigned)num_sort_tiles(a.n, ITEMS)),
+                            dim3(SORT_THREADS), smem, s, a));
     return 1;
 }
 
@@ -452,7 +497,8 @@ size_t sort_temp_bytes(size_t n) {
     b += align_up((size_t)MAX_PASSES * RADIX * 4, 128);
     b += align_up((size_t)MAX_PASSES * 2 * 4, 128);
     // 8 passes of large tiles (64-bit keys) >= 4 passes of small tiles (32-bit keys): same bytes + rounding
-    b += align_up((size_t)MAX_PASSES * (num_sort_tiles(n, ITEMS_LARGE) + 1) * RADIX * 4, 128);
+    const size_t tiles = num_sort_tiles(n, ITEMS_LARGE) + 1;
+    b += align_up((size_t)MAX_PASSES * (tiles + num_groups(tiles) + 1) * RADIX * 4, 128);
     return b + 128;
 }
 
@@ -471,8 +517,6 @@ int launch_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint
     int launches = 0;
     if (events) cudaEventRecord(events[0], s);
     launches += launch_histogram<uint2>(reinterpret_cast<const uint2*>(keys_a), n, end_bit, passes, L.hist, s);
-    scan_histograms_kernel<<<1, RADIX, 0, s>>>(L.hist, passes);
-    ++launches;
     if (events) cudaEventRecord(events[1], s);
     uint64_t* kin = keys_a; uint32_t* vin = vals_a;
     uint64_t* kout = keys_b; uint32_t* vout = vals_b;
@@ -481,8 +525,9 @@ int launch_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint
         a.keys_in = kin; a.vals_in = vin; a.keys_out = kout; a.vals_out = vout; a.n = n;
         a.shift = ps * RADIX_BITS;
         a.nbits = std::min(RADIX_BITS, end_bit - a.shift);
-        a.digit_offsets = L.hist + ps * RADIX;
+        a.digit_counts = L.hist + ps * RADIX;
         a.status = L.status + (size_t)ps * tiles * RADIX;
+        a.gstat = L.gstat + (size_t)ps * num_groups(tiles) * RADIX;
         a.ticket = L.tickets + ps;
         a.error_flag = L.tickets + MAX_PASSES;
         a.expand_low = nullptr; a.keys_out64 = nullptr;
@@ -519,8 +564,6 @@ int launch_sort32(const Sort32Plan& p, cudaStream_t s, cudaEvent_t* events) {
     if (!p.hist_ready) {
         launches += launch_histogram<uint32_t>(p.keys_in, p.n, p.end_bit, passes, L.hist, s);
     }
-    scan_histograms_kernel<<<1, RADIX, 0, s>>>(L.hist, passes);
-    ++launches;
     if (events) cudaEventRecord(events[1], s);
     const uint32_t* kin = p.keys_in;
     const uint32_t* vin = p.vals_in;
@@ -530,8 +573,9 @@ int launch_sort32(const Sort32Plan& p, cudaStream_t s, cudaEvent_t* events) {
         a.keys_in = kin; a.vals_in = vin; a.n = p.n;
         a.shift = ps * RADIX_BITS;
         a.nbits = std::min(RADIX_BITS, p.end_bit - a.shift);
-        a.digit_offsets = L.hist + ps * RADIX;
+        a.digit_counts = L.hist + ps * RADIX;
         a.status = L.status + (size_t)ps * tiles * RADIX;
+        a.gstat = L.gstat + (size_t)ps * num_groups(tiles) * RADIX;
         a.ticket = L.tickets + ps;
         a.error_flag = L.tickets + MAX_PASSES;
         a.expand_low = nullptr; a.keys_out64 = nullptr;

@@ -161,6 +161,76 @@ def cpu_reference(workload, frames, threads=None, P=None):
     return dict(ms=[t * 1e3 for t in times], threads=threads, R=r.num_rendered, stage=stage, P=sc.P, cfg=cfg)
 
 
+def gpu_reference(sc, cfg, dev, frames=20, warmup=3):
+    """Second baseline of north_star: the reference's OWN in-tree rasterizer (apps/gsrast/gscuda/GSCuda.cu,
+    compiled unmodified for sm_100a into oracle/_ref) on this GPU, on the same scene in the viewer's buffer
+    layout — beside OUR library run in GSRast-compat mode on exactly the same device buffers (same semantics,
+    bit-identical radii/keys/ranges, see tests/test_gpu_reference_live.py).  Serial frames, CUDA events."""
+    import numpy as np
+    import torch
+
+    from gsrast_b200 import _lib, camera
+    from gsrast_b200.views import ViewRenderer
+    from oracle import gscuda_ref
+
+    if not gscuda_ref.available():
+        return {"unavailable": "oracle/_ref/libgscuda_ref.so not built (needs /root/reference at build time)"}
+    W, H = cfg["W"], cfg["H"]
+    cam = camera.default_camera(W, H)
+    ref = gscuda_ref.RefRenderer(sc, W, H, device=dev, use_rects=True)
+    view = torch.from_numpy(cam.viewmatrix).to(dev)
+    proj = torch.from_numpy(cam.projmatrix).to(dev)
+    cpos = torch.from_numpy(cam.cam_pos).to(dev)
+    ptr = lambda x: None if x is None else x.data_ptr()  # noqa: E731
+
+    def ref_frame():
+        gscuda_ref.lib().gscuda_ref_forward(ref.cbs[0], None, ref.cbs[1], None, ref.cbs[2], None, ref.P, 3, 16,
+                                            ptr(ref.bg), W, H, ptr(ref.means), ptr(ref.shs), ptr(ref.colors),
+                                            ptr(ref.opac), ptr(ref.scales), 1.0, ptr(ref.rot), None, ptr(view),
+                                            ptr(proj), ptr(cpos), cam.tan_fovx, cam.tan_fovy, 0, ptr(ref.out), None,
+                                            ptr(ref.rects), None, None)
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    for _ in range(warmup):
+        ref_frame()
+    ref_ms = timed(ref_frame, frames)
+    R_ref = int(ref.state()["num_rendered"])
+    del ref
+    torch.cuda.empty_cache()
+
+    # ours, GSRast-compat, same layout (vec4 means/scales, raw PLY SH block), one view at a time
+    means4, scales4, rot, opac, shs_raw = sc.gsrast_layout()
+    t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    vr = ViewRenderer(P=sc.P, D=3, M=16, means3D=t(means4), shs=t(shs_raw), colors_precomp=t(sc.colors_precomp),
+                      opacities=t(opac), scales=t(scales4), rotations=t(rot),
+                      background=torch.zeros(3, dtype=torch.float32, device=dev), width=W, height=H, compat=True)
+    out = torch.empty((1, 3, H, W), dtype=torch.float32, device=dev)
+    packed = np.stack([cam.packed()]).astype(np.float32)
+    nr = [0]
+
+    def our_frame():
+        nr[0] = vr.render(packed, cam.tan_fovx, cam.tan_fovy, out=out)[1][0]
+
+    for _ in range(warmup):
+        our_frame()
+    our_ms = timed(our_frame, frames)
+    vr.close()
+    return {"value": 1e3 / ref_ms, "unit": "frames/s", "ms_per_frame": ref_ms, "num_rendered": R_ref,
+            "kind": "reference's in-tree gscuda::forward (GSCuda.cu + AuxBuffer.cu compiled unmodified, sm_100a, CUB sort)",
+            "ours_same_semantics": {"value": 1e3 / our_ms, "unit": "frames/s", "ms_per_frame": our_ms,
+                                    "num_rendered": int(nr[0]), "mode": "GSR_FLAG_GSRAST_COMPAT, serial single views"},
+            "speedup": ref_ms / our_ms, "frames": frames}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -195,6 +265,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
     ap.add_argument("--gather", action="store_true", help="also time the NCCL gather of frames to rank 0 (N>1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the in-tree gscuda (oracle/_ref) GPU baseline")
     ap.add_argument("--cpu-frames", type=int, default=3)
     ap.add_argument("--simple-blend", action="store_true")
     ap.add_argument("--P", type=int, default=None, help="override the Gaussian count (debug only; invalidates the metric)")
@@ -402,6 +473,13 @@ def main():
                    "sample": "%d full %s frame(s) of the CPU oracle, median %.0f ms" % (len(c["ms"]), args.workload, m),
                    "stage_ms": {k: v * 1e3 for k, v in c["stage"].items()}}
 
+        gref = None
+        if not args.no_gpu_reference and not args.no_cpu_baseline and world == 1:
+            try:
+                gref = gpu_reference(sc, cfg, dev)
+            except Exception as ex:  # the baseline must never take the bench line down
+                gref = {"unavailable": "%s: %s" % (type(ex).__name__, ex)}
+
         total_frames = K * world
         line = {
             "metric": METRIC, "value": total_frames / (dev_ms / 1e3), "unit": "frames/s", "n_gpus": world, "steps": K,
@@ -420,6 +498,8 @@ def main():
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if gref:
+            line["gpu_reference"] = gref
         if gather_ms is not None:
             line["gather"] = {"value": total_frames / (gather_ms / 1e3), "unit": "frames/s",
                               "note": "render + NCCL gather of fp32 frames to rank 0"}

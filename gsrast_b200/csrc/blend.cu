@@ -127,7 +127,10 @@ __device__ __forceinline__ float max_power_in_box(float a, float b, float c, flo
 //   [0] x, y, a', b'      (conic pre-scaled by log2(e): power*log2(e) = a' dx^2 + c' dy^2 + b' dx dy)
 //   [1] c', opacity, r, g
 //   [2] b, -, -, -
-__global__ void __launch_bounds__(BLEND_THREADS) blend_culled_kernel(const BlendParams p) {
+#ifndef GSR_BLEND_MINB
+#define GSR_BLEND_MINB 5
+#endif
+__global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_kernel(const BlendParams p) {
     __shared__ float4 s_splat[BATCH * 3];
     __shared__ unsigned char s_mask[BATCH];                     // bit w: splat can reach warp w's 8x4 sub-rectangle
     __shared__ unsigned char s_list[BLEND_THREADS / 32][BATCH]; // per warp: staged indices of its candidates
@@ -149,24 +152,43 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_culled_kernel(const Blend
     const int total = (int)(range.y - range.x);
     const int rounds = (total + BATCH - 1) / BATCH;
 
-    bool done = !inside;
-    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+    // pixels outside the image start "terminated" (negative T, see the inner loop)
+    float T = inside ? 1.0f : -1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
     uint32_t last = 0;
-    bool warp_done = __all_sync(0xffffffffu, done);
+    bool warp_done = __all_sync(0xffffffffu, !inside);
+
+    // Software pipeline: the gather of batch r+1 (sorted id -> mean, conic, colour: two dependent
+    // memory round trips) is issued into registers before batch r is blended and lands while it runs.
+    float2 n_xy = make_float2(0.f, 0.f);
+    float4 n_co = make_float4(0.f, 0.f, 0.f, 0.f);
+    float n_c0 = 0.f, n_c1 = 0.f, n_c2 = 0.f;
+    if (tid < total) {
+        const uint32_t id = __ldg(p.point_list + range.x + tid);
+        n_xy = __ldg(reinterpret_cast<const float2*>(p.means2D) + id);
+        n_co = __ldg(reinterpret_cast<const float4*>(p.conic_opacity) + id);
+        const float* col = p.colors + (size_t)id * 3;
+        n_c0 = __ldg(col); n_c1 = __ldg(col + 1); n_c2 = __ldg(col + 2);
+    }
 
     for (int r = 0; r < rounds; ++r) {
         if (__syncthreads_and(warp_done)) break;
         const int progress = r * BATCH + tid;
         uint32_t m = 0;
-        if (progress < total) {
-            const uint32_t id = __ldg(p.point_list + range.x + progress);
-            const float2 xy = __ldg(reinterpret_cast<const float2*>(p.means2D) + id);
-            const float4 co = __ldg(reinterpret_cast<const float4*>(p.conic_opacity) + id);
+        const float2 xy = n_xy;
+        const float4 co = n_co;
+        const float cr = n_c0, cg = n_c1, cb = n_c2;
+        if (progress + BATCH < total) {
+            const uint32_t id = __ldg(p.point_list + range.x + progress + BATCH);
+            n_xy = __ldg(reinterpret_cast<const float2*>(p.means2D) + id);
+            n_co = __ldg(reinterpret_cast<const float4*>(p.conic_opacity) + id);
             const float* col = p.colors + (size_t)id * 3;
+            n_c0 = __ldg(col); n_c1 = __ldg(col + 1); n_c2 = __ldg(col + 2);
+        }
+        if (progress < total) {
             const float a = co.x, b = co.y, c = co.z, o = co.w;
             s_splat[3 * tid + 0] = make_float4(xy.x, xy.y, -0.5f * LOG2E * a, -LOG2E * b);
-            s_splat[3 * tid + 1] = make_float4(-0.5f * LOG2E * c, o, __ldg(col), __ldg(col + 1));
-            s_splat[3 * tid + 2] = make_float4(__ldg(col + 2), 0.f, 0.f, 0.f);
+            s_splat[3 * tid + 1] = make_float4(-0.5f * LOG2E * c, o, cr, cg);
+            s_splat[3 * tid + 2] = make_float4(cb, 0.f, 0.f, 0.f);
             // ---- which sub-rectangles can see this splat with alpha >= 1/255 ? ----------
             // alpha >= 1/255  <=>  power >= -ln(255*o) =: thr.  First the axis-aligned bounding box of that
             // ellipse (half extents sqrt(-2 thr c/det), sqrt(-2 thr a/det)) picks candidate sub-rectangles,
@@ -218,9 +240,14 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_culled_kernel(const Blend
                 n += __popc(bits);
             }
             __syncwarp();
+            // Branch-free inner loop.  A terminated pixel carries its final transmittance as a NEGATIVE T:
+            // then w = alpha*T and T - w are negative, "T - w >= t_min" fails, nothing is blended, and
+            // no separate `done` flag has to be tested.  Per candidate: 2 LDS.128, 8 FP32 for the exponent,
+            // MUFU.EX2, 4 FP32 + 3 FSETP for alpha / transmittance, then predicated: LDS, 3 FFMA, T, last.
             const uint32_t rbase = (uint32_t)(r * BATCH + 1);
             for (int i0 = 0; i0 < n; i0 += 16) {
                 const int i1 = min(n, i0 + 16);
+#pragma unroll 2
                 for (int i = i0; i < i1; ++i) {
                     const int j = my_list[i];
                     const float4* sp = s_splat + 3 * j;
@@ -229,26 +256,28 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_culled_kernel(const Blend
                     const float dx = a.x - pixf_x, dy = a.y - pixf_y;
                     const float p2 = fmaf(a.z, dx * dx, fmaf(b.x, dy * dy, a.w * (dx * dy)));
                     const float alpha = fminf(0.99f, b.y * ex2_approx(p2));
-                    if (done || p2 > 0.0f || alpha < ALPHA_MIN) continue;
-                    const float test_T = T * (1.0f - alpha);
-                    if (test_T < p.t_min) {
-                        done = true;
-                        continue;
-                    }
                     const float w = alpha * T;
-                    C0 = fmaf(b.z, w, C0);
-                    C1 = fmaf(b.w, w, C1);
-                    C2 = fmaf(sp[2].x, w, C2);
-                    T = test_T;
-                    last = rbase + (uint32_t)j;
+                    const float test_T = T - w;  // T*(1-alpha)
+                    const bool cand = (p2 <= 0.0f) && (alpha >= ALPHA_MIN);
+                    const bool ok = cand && (test_T >= p.t_min);
+                    const bool term = cand && !(test_T >= p.t_min);  // also true again later: idempotent below
+                    if (ok) {
+                        C0 = fmaf(b.z, w, C0);
+                        C1 = fmaf(b.w, w, C1);
+                        C2 = fmaf(sp[2].x, w, C2);
+                        T = test_T;
+                        last = rbase + (uint32_t)j;
+                    }
+                    if (term) T = __uint_as_float(__float_as_uint(T) | 0x80000000u);  // T = -|T|: stop, keep final T
                 }
-                if (__all_sync(0xffffffffu, done)) {
+                if (__all_sync(0xffffffffu, T <= 0.0f)) {
                     warp_done = true;
                     break;
                 }
             }
         }
     }
+    T = fabsf(T);
     if (inside) {
         const size_t pix = (size_t)pix_y * p.W + pix_x;
         const size_t plane = (size_t)p.W * p.H;

@@ -48,6 +48,7 @@ struct Lane {
     float* cam_dev = nullptr;   // [CAM_FLOATS]
     float* cam_host = nullptr;  // pinned
     float* frame_dev = nullptr; // [3*H*W], only for host-output rendering
+    int* rects = nullptr;       // [2*P], GSRast-compat only: the viewer always passes _rects (GSGaussians.cpp:137,204)
     cudaEvent_t cam_free = nullptr;  // cam_host may be overwritten once this fired
     cudaEvent_t done = nullptr;
     bool cam_pending = false;
@@ -86,6 +87,7 @@ void lane_destroy(Lane& l) {
     if (l.cam_dev) cudaFree(l.cam_dev);
     if (l.cam_host) cudaFreeHost(l.cam_host);
     if (l.frame_dev) cudaFree(l.frame_dev);
+    if (l.rects) cudaFree(l.rects);
     if (l.cam_free) cudaEventDestroy(l.cam_free);
     if (l.done) cudaEventDestroy(l.done);
     release_slot(l.slot);
@@ -118,6 +120,10 @@ int render_one(Renderer* r, Lane& l, const float* cam36, float tan_fovx, float t
     a.viewmatrix = l.cam_dev; a.projmatrix = l.cam_dev + 16; a.cam_pos = l.cam_dev + 32;
     a.tan_fovx = tan_fovx; a.tan_fovy = tan_fovy;
     a.out_color = out_dev;
+    if (compat) {
+        if (!l.rects && r->P > 0) GSR_CUDA_TRY(cudaMalloc(&l.rects, (size_t)r->P * 2 * sizeof(int)));
+        a.rects = l.rects;
+    }
     a.stream = l.stream;
     a.flags = r->flags;
     a.timings = times;

@@ -49,7 +49,8 @@ def test_view_batch_compat_mode():
                       compat=True)
     out, nr = vr.render([cam], cam.tan_fovx, cam.tan_fovy)
     torch.cuda.synchronize()
-    single = run_cuda(sc, cam, compat=True)
+    # the renderer mirrors GSGaussians, which always passes its _rects buffer (GSGaussians.cpp:137,204)
+    single = run_cuda(sc, cam, compat=True, use_rects=True)
     assert nr[0] == single["num_rendered"] and np.array_equal(out[0].cpu().numpy(), single["out_color"])
 
 

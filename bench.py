@@ -45,23 +45,40 @@ WORKLOADS = {
 }
 
 
-def algorithmic_bytes(P, P_visible, P_culled, R, tiles, depth_passes, tile_passes, precomp):
-    """SURVEY.md §8(d) per-unit figures, plus the bytes the split sort's own launches are defined to move
-    (DESIGN.md §4): depth passes 16 B/Gaussian (first one 12: the ids are generated), tile passes
-    16 B/pair, the last one 8 + 4 (depth gather) read + 12 written."""
+def algorithmic_bytes(P, P_visible, P_culled, R, tiles, depth_passes, tile_passes, precomp, Rc=0, survey_passes=6):
+    """SURVEY.md §8(d) per-unit figures, plus the bytes this design's own launches are defined to move
+    (DESIGN.md §4): depth passes 16 B/Gaussian (first one 12: the ids are generated).
+    Radix binning (Rc == 0): tile passes 16 B/pair, the last one 8 + 4 (depth gather) read + 12 written.
+    Bin expansion (Rc = (Gaussian, bin) records): duplication writes 8 B/record, every bin-digit pass moves
+    16 B/record, the count pass reads 4 + 8 B/record, the fill pass 4 + 8 + 4 B/record and writes the result,
+    12 B/pair."""
     per_vis = (44 + 12 + 48) if precomp else 284
-    passes = depth_passes + tile_passes
-    return {
+    d = {
         "preprocess": per_vis * P_visible + 20 * P_culled + 4 * P,   # + the 4-byte depth key
         "scan": 0,
-        "duplicate": 20 * P_visible + 8 * R,                         # 32-bit tile key + id per pair
-        "sort_survey": (8 + passes * 24) * R,                        # §8(d): 64-bit keys, every pass over R pairs
-        "sort_moved": 4 * P + (16 * depth_passes - 4) * P + (16 * (tile_passes - 1) + 24) * R,
+        "sort_survey": (8 + survey_passes * 24) * R,                 # §8(d): 64-bit keys, 6 CUB passes over R pairs
         "depth_pass": 16 * P,
-        "tile_pass": 16 * R,
-        "tile_pass_last": 24 * R,
-        "ranges": 8 * R + 8 * tiles,
     }
+    depth_moved = 4 * P + (16 * depth_passes - 4) * P
+    if Rc:
+        d.update({
+            "duplicate": 20 * P_visible + 8 * Rc,
+            "bin_pass": 16 * Rc,
+            "expand_count": 12 * Rc,
+            "expand_fill": 16 * Rc + 12 * R + 4 * tiles,
+            "ranges": 0,
+        })
+        d["expand"] = d["expand_count"] + d["expand_fill"] + 8 * tiles
+        d["sort_moved"] = depth_moved + tile_passes * d["bin_pass"] + d["expand"]
+    else:
+        d.update({
+            "duplicate": 20 * P_visible + 8 * R,                     # 32-bit tile key + id per pair
+            "tile_pass": 16 * R,
+            "tile_pass_last": 24 * R,
+            "ranges": 8 * R + 8 * tiles,
+        })
+        d["sort_moved"] = depth_moved + (16 * (tile_passes - 1) + 24) * R
+    return d
 
 
 class ClockSampler:
@@ -268,6 +285,8 @@ def main():
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the in-tree gscuda (oracle/_ref) GPU baseline")
     ap.add_argument("--cpu-frames", type=int, default=3)
     ap.add_argument("--simple-blend", action="store_true")
+    ap.add_argument("--radix-binning", action="store_true",
+                    help="A/B: radix passes over all pairs instead of the bin expansion (GSR_FLAG_RADIX_BINNING)")
     ap.add_argument("--P", type=int, default=None, help="override the Gaussian count (debug only; invalidates the metric)")
     args = ap.parse_args()
     if args.workload is None:
@@ -300,7 +319,7 @@ def main():
     base = "C2" if args.workload == "C4" else args.workload
     sc, cfg = scene.make_config_scene(base, P=args.P)
     W, H = cfg["W"], cfg["H"]
-    flags = _lib.FLAG_BLEND_SIMPLE if args.simple_blend else 0
+    flags = (_lib.FLAG_BLEND_SIMPLE if args.simple_blend else 0) | (_lib.FLAG_RADIX_BINNING if args.radix_binning else 0)
     t_up = time.time()
     vr = ViewRenderer.from_scene(sc, W, H, device=dev, flags=flags)
     torch.cuda.synchronize()
@@ -390,13 +409,14 @@ def main():
             if i >= 2:
                 stage_runs.append(tm)
         keys = ("preprocess_ms", "scan_ms", "duplicate_ms", "sort_ms", "ranges_ms", "blend_ms", "total_ms",
-                "sort_hist_ms", "depth_sort_ms")
+                "sort_hist_ms", "depth_sort_ms", "expand_ms")
         st = {k: statistics.mean(r[k] for r in stage_runs) for k in keys}
         passes = stage_runs[0]["sort_passes"]
         dpasses = stage_runs[0]["depth_passes"]
         tpasses = passes - dpasses
         pass_ms = [statistics.mean(r["sort_pass_ms"][i] for r in stage_runs) for i in range(passes)]
         R = stage_runs[0]["num_rendered"]
+        Rc = stage_runs[0]["num_coarse"] if stage_runs[0]["binning_mode"] == 0 else 0
         launches_per_frame = stage_runs[0]["kernel_launches"]
         # visible count from the geometry state of lane 0 is not exposed; recompute cheaply on the device
         from gsrast_b200 import rasterizer as Rz
@@ -410,7 +430,10 @@ def main():
         del g
         torch.cuda.empty_cache()
         tiles = ((W + 15) // 16) * ((H + 15) // 16)
-        ab = algorithmic_bytes(sc.P, P_vis, sc.P - P_vis, R, tiles, dpasses, tpasses, sc.colors_precomp is not None)
+        from gsrast_b200.rasterizer import get_higher_msb
+
+        ab = algorithmic_bytes(sc.P, P_vis, sc.P - P_vis, R, tiles, dpasses, tpasses, sc.colors_precomp is not None, Rc=Rc,
+                               survey_passes=(32 + get_higher_msb(tiles) + 7) // 8)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -422,37 +445,53 @@ def main():
         def gbs(b, ms):
             return (b / 1e9) / (ms / 1e3) if ms and ms > 0 else None
 
+        # "sort" = everything between the duplication and the blend that produces the sorted per-tile lists: the
+        # depth half (P Gaussians, before duplication) + the tile half — bin-digit passes over the (Gaussian, bin)
+        # records and the bin expansion (default), or tile-digit passes over the R pairs (--radix-binning).
+        # "GB/s" rates it by SURVEY §8(d)'s 152 B/pair (what the reference's 6-pass CUB sort of R pairs moves);
+        # "GB/s_moved" by the bytes this design is defined to move.
+        sort_total_ms = st["sort_ms"] + st["depth_sort_ms"] + st["expand_ms"]
         stages = {
             "preprocess": {"ms": st["preprocess_ms"], "GB/s": gbs(ab["preprocess"], st["preprocess_ms"])},
             "scan": {"ms": st["scan_ms"]},
             "duplicate": {"ms": st["duplicate_ms"], "GB/s": gbs(ab["duplicate"], st["duplicate_ms"])},
-            # the LSD sort = depth half (P Gaussians, before duplication) + tile half (R pairs).  "GB/s" rates the
-            # whole sort by SURVEY §8(d)'s 152 B/pair (what a 6-pass sort of R pairs moves); "GB/s_moved" by the
-            # bytes the split design is defined to move.
-            "sort": {"ms": st["sort_ms"] + st["depth_sort_ms"], "depth_ms": st["depth_sort_ms"],
-                     "tile_ms": st["sort_ms"],
-                     "GB/s": gbs(ab["sort_survey"], st["sort_ms"] + st["depth_sort_ms"]),
-                     "GB/s_moved": gbs(ab["sort_moved"], st["sort_ms"] + st["depth_sort_ms"]),
-                     "hist_ms": st["sort_hist_ms"], "pass_ms": pass_ms, "passes": passes, "depth_passes": dpasses},
-            "ranges": {"ms": st["ranges_ms"], "GB/s": gbs(ab["ranges"], st["ranges_ms"])},
+            "sort": {"ms": sort_total_ms, "depth_ms": st["depth_sort_ms"], "tile_ms": st["sort_ms"] + st["expand_ms"],
+                     "bin_pass_ms": st["sort_ms"] if Rc else None, "expand_ms": st["expand_ms"] if Rc else None,
+                     "GB/s": gbs(ab["sort_survey"], sort_total_ms),
+                     "GB/s_moved": gbs(ab["sort_moved"], sort_total_ms),
+                     "hist_ms": st["sort_hist_ms"], "pass_ms": pass_ms, "passes": passes, "depth_passes": dpasses,
+                     "binning": "bin expansion" if Rc else "radix", "num_coarse": Rc},
+            "ranges": {"ms": st["ranges_ms"], "GB/s": gbs(ab["ranges"], st["ranges_ms"]) if not Rc else None},
             "blend": {"ms": st["blend_ms"]},
             "frame_serial_ms": st["total_ms"],
         }
+        if Rc:
+            stages["expand"] = {"ms": st["expand_ms"], "GB/s": gbs(ab["expand"], st["expand_ms"])}
         for v in stages.values():
             if isinstance(v, dict) and v.get("GB/s"):
                 v["frac_of_peak"] = v["GB/s"] / peak
-        pre_sort_b = ab["preprocess"] + ab["duplicate"] + ab["sort_survey"] + ab["ranges"]
+        pre_sort_b = ab["preprocess"] + ab["duplicate"] + ab["sort_survey"] + (ab["ranges"] if not Rc else 8 * R + 8 * tiles)
         pre_sort_ms = (st["preprocess_ms"] + st["scan_ms"] + st["depth_sort_ms"] + st["duplicate_ms"] + st["sort_ms"] +
-                       st["ranges_ms"])
+                       st["expand_ms"] + st["ranges_ms"])
         stages["preprocess_plus_sort"] = {"ms": pre_sort_ms, "GB/s": gbs(pre_sort_b, pre_sort_ms),
-                                          "frac_of_peak": gbs(pre_sort_b, pre_sort_ms) / peak}
-        # dominant HBM kernel: a single launch — preprocess, duplication, or a tile-digit onesweep pass
+                                          "frac_of_peak": gbs(pre_sort_b, pre_sort_ms) / peak,
+                                          "note": "SURVEY 8(d) algorithmic bytes of preprocess + duplicate + 6-pass sort + "
+                                                  "ranges over the time of everything before the blend"}
+        # dominant HBM kernel: a single launch — preprocess, the expansion's fill pass / a tile-digit onesweep
+        # pass, or the duplication
         tile_ms = pass_ms[dpasses:]
-        osw = "onesweep_kernel<u32> (mean of %d tile-digit passes over R pairs)" % tpasses
         cand = {"preprocess_kernel": (ab["preprocess"], st["preprocess_ms"]),
-                osw: ((ab["tile_pass"] * (tpasses - 1) + ab["tile_pass_last"]) / max(tpasses, 1), statistics.mean(tile_ms)),
                 "duplicate_sorted_kernel": (ab["duplicate"], st["duplicate_ms"])}
-        share = {"preprocess_kernel": st["preprocess_ms"], "duplicate_sorted_kernel": st["duplicate_ms"], osw: sum(tile_ms)}
+        share = {"preprocess_kernel": st["preprocess_ms"], "duplicate_sorted_kernel": st["duplicate_ms"]}
+        if Rc:
+            # the count / scan kernels of the expansion are a small share; the fill pass is rated on the expansion's
+            # whole time (an upper bound of its own), so its fraction is a lower bound
+            cand["expand_fill_kernel"] = (ab["expand_fill"], st["expand_ms"])
+            share["expand_fill_kernel"] = st["expand_ms"]
+        else:
+            osw = "onesweep_kernel<u32> (mean of %d tile-digit passes over R pairs)" % tpasses
+            cand[osw] = ((ab["tile_pass"] * (tpasses - 1) + ab["tile_pass_last"]) / max(tpasses, 1), statistics.mean(tile_ms))
+            share[osw] = sum(tile_ms)
         dom = max(share, key=share.get)
         roof = {"bound": "hbm", "kernel": dom, "achieved": gbs(*cand[dom]), "peak": peak, "unit": "GB/s",
                 "frac": gbs(*cand[dom]) / peak, "traffic": None, "peak_source": peak_src,
@@ -490,7 +529,9 @@ def main():
                        "views_per_step": world, "parallelism": "views sharded, scene replicated" if world > 1 else "1 GPU",
                        "l2": "no flush: the per-frame working set (%.2f GB attributes + scratch) exceeds the 126 MB L2"
                              % ((sc.P * 236 + sc.P * 80 + R * 24) / 1e9),
-                       "blend": "simple" if args.simple_blend else "culled", "scene_upload_s": upload_s},
+                       "blend": "simple" if args.simple_blend else "culled",
+                       "binning": "radix" if not Rc else "bin expansion", "num_coarse": Rc,
+                       "scene_upload_s": upload_s},
             "e2e": {"value": total_frames / (e2e_ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": 144,
                     "d2h_bytes_per_step": frame_bytes, "ms_per_step": e2e_ms / K, "checksum": checksum},
             "gpu_launches": launches_per_frame * K * 1,

@@ -15,6 +15,7 @@ ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_void_p)
 
 FLAG_GSRAST_COMPAT = 0x1
 FLAG_BLEND_SIMPLE = 0x2
+FLAG_RADIX_BINNING = 0x4
 
 ERR_INVALID_ARG = -1000
 ERR_ALLOC_FAILED = -1001
@@ -27,7 +28,8 @@ class StageTimes(C.Structure):
                 ("preprocess_ms", "scan_ms", "duplicate_ms", "sort_ms", "ranges_ms", "blend_ms", "total_ms")] + \
                [("num_rendered", C.c_int), ("sort_passes", C.c_int), ("kernel_launches", C.c_int),
                 ("sort_hist_ms", C.c_float), ("sort_pass_ms", C.c_float * 8),
-                ("depth_sort_ms", C.c_float), ("depth_passes", C.c_int)]
+                ("depth_sort_ms", C.c_float), ("depth_passes", C.c_int),
+                ("expand_ms", C.c_float), ("num_coarse", C.c_int), ("binning_mode", C.c_int)]
 
     def as_dict(self):
         d = {n: getattr(self, n) for n, _ in self._fields_}
@@ -73,7 +75,7 @@ class GeometryState(C.Structure):
                  "point_offsets", "block_sums")] + [("scan_size", C.c_size_t)] + \
                [("depth_keys", C.c_void_p), ("tile_rects", C.c_void_p), ("depth_sort_keys", C.c_void_p * 2), ("depth_sort_ids", C.c_void_p * 2),
                 ("depth_sort_space", C.c_void_p), ("depth_sort_size", C.c_size_t),
-                ("sorted_rects", C.c_void_p), ("sorted_block_sums", C.c_void_p)]
+                ("sorted_rects", C.c_void_p), ("sorted_block_sums", C.c_void_p), ("coarse_block_sums", C.c_void_p)]
 
 
 class ImageState(C.Structure):

@@ -28,14 +28,22 @@ constexpr int DUP_GAUSS = DUP_GPT * PRE_THREADS;
 // (4.2 M Gaussians) take a single round of one warp scan + one cross-warp scan.
 __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(uint32_t* __restrict__ block_sums, int n,
                                                                        uint32_t* __restrict__ total_dev,
-                                                                       volatile uint32_t* total_host) {
+                                                                       volatile uint32_t* total_host,
+                                                                       const uint32_t* __restrict__ sums2) {
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
     __shared__ uint32_t s_carry;
+    __shared__ uint32_t s_total2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_carry = 0;
+    if (tid == 0) { s_carry = 0; s_total2 = 0; }
     gsr_pdl_wait();
     gsr_pdl_launch_dependents();
     __syncthreads();
+    if (sums2) {  // plain reduction of the second array (its loads overlap the scan below)
+        uint32_t t2 = 0;
+        for (int i = tid; i < n; i += SCAN_THREADS) t2 += __ldg(sums2 + i);
+        t2 = __reduce_add_sync(0xffffffffu, t2);
+        if (lane == 0 && t2) atomicAdd(&s_total2, t2);
+    }
     constexpr int CHUNK = SCAN_THREADS * SCAN_ITEMS;
     for (int base = 0; base < n; base += CHUNK) {
         const int i0 = base + tid * SCAN_ITEMS;
@@ -97,7 +105,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(uint32_t*
         const uint32_t total = s_carry;
         *total_dev = total;
         if (total_host) {
-            *total_host = total;
+            if (sums2) total_host[1] = s_total2;
+            total_host[0] = total;
             __threadfence_system();
         }
     }
@@ -111,6 +120,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(uint32_t*
 //      cub::DeviceScan::InclusiveSum leaves in pointOffsets (GSCuda.cu:771), which the Inspector reads
 //      (Inspector.cpp:174-188).  The pipeline itself consumes the scan in depth order, so this is on
 //      the side.  `block_offsets` are the exclusive offsets of preprocess' 256-Gaussian blocks.
+template <bool COARSE>
 __global__ void __launch_bounds__(PRE_THREADS) gather_rects_kernel(const int P, const uint32_t* __restrict__ sorted_ids,
                                                                    const uint2* __restrict__ tile_rects,
                                                                    uint2* __restrict__ sorted_rects,
@@ -131,7 +141,8 @@ __global__ void __launch_bounds__(PRE_THREADS) gather_rects_kernel(const int P, 
         if (i < P) {
             // the tile rect preprocess computed with getRect (GSCuda.cu:237-259; duplicateWithKeys recomputes
             // the same rect, :445-458).  Gaussians that emit nothing (radii <= 0, :440-443) carry an empty rect.
-            const uint2 rec = __ldg(tile_rects + __ldg(sorted_ids + i));
+            uint2 rec = __ldg(tile_rects + __ldg(sorted_ids + i));
+            if (COARSE) rec = coarse_rect(rec);  // bin expansion: the duplication emits (bin, Gaussian) records
             sorted_rects[i] = rec;
             cnt += (rec.y >> 16) * (rec.y & 0xffffu);
         }
@@ -376,9 +387,9 @@ __global__ void __launch_bounds__(256) identify_ranges_kernel(const size_t n, co
 }  // namespace
 
 int launch_scan_block_sums(uint32_t* block_sums, int num_blocks, uint32_t* total_dev, uint32_t* total_host_mapped,
-                           cudaStream_t s) {
+                           cudaStream_t s, const uint32_t* sums2) {
     cudaError_t e = launch_pdl(scan_block_sums_kernel, dim3(1), dim3(SCAN_THREADS), 0, s, block_sums, num_blocks, total_dev,
-                               (volatile uint32_t*)total_host_mapped);
+                               (volatile uint32_t*)total_host_mapped, sums2);
     return e == cudaSuccess ? 1 : -(int)e;
 }
 
@@ -386,12 +397,16 @@ int num_dup_blocks(int P) { return ((P > 0 ? P : 0) + DUP_GAUSS - 1) / DUP_GAUSS
 
 int launch_gather_rects(int P, const uint32_t* sorted_ids, const uint32_t* tile_rects, uint32_t* sorted_rects,
                         uint32_t* block_sums, const uint32_t* tiles_touched, const uint32_t* block_offsets,
-                        uint32_t* point_offsets, cudaStream_t s) {
+                        uint32_t* point_offsets, bool coarse, cudaStream_t s) {
     if (P <= 0) return 0;
     const int blocks = num_dup_blocks(P);
-    cudaError_t e = launch_pdl(gather_rects_kernel, dim3(blocks), dim3(PRE_THREADS), 0, s, P, sorted_ids,
-                               reinterpret_cast<const uint2*>(tile_rects), reinterpret_cast<uint2*>(sorted_rects),
-                               block_sums, tiles_touched, block_offsets, point_offsets);
+    cudaError_t e =
+        coarse ? launch_pdl(gather_rects_kernel<true>, dim3(blocks), dim3(PRE_THREADS), 0, s, P, sorted_ids,
+                            reinterpret_cast<const uint2*>(tile_rects), reinterpret_cast<uint2*>(sorted_rects),
+                            block_sums, tiles_touched, block_offsets, point_offsets)
+               : launch_pdl(gather_rects_kernel<false>, dim3(blocks), dim3(PRE_THREADS), 0, s, P, sorted_ids,
+                            reinterpret_cast<const uint2*>(tile_rects), reinterpret_cast<uint2*>(sorted_rects),
+                            block_sums, tiles_touched, block_offsets, point_offsets);
     return e == cudaSuccess ? 1 : -(int)e;
 }
 

@@ -143,6 +143,7 @@ size_t gsr_geometry_state_map(char* chunk, int P, gsr_geometry_state* g) {
     obtain(c, st.depth_sort_space, st.depth_sort_size);
     obtain(c, st.sorted_rects, n * 2 * sizeof(uint32_t));
     obtain(c, st.sorted_block_sums, st.scan_size);
+    obtain(c, st.coarse_block_sums, st.scan_size);
     if (g) *g = st;
     return (size_t)(c - chunk);
 }
@@ -167,7 +168,7 @@ size_t gsr_binning_state_map(char* chunk, size_t R, gsr_binning_state* b) {
     obtain(c, st.point_list_keys, R * sizeof(uint64_t));
     obtain(c, st.point_list_unsorted, R * sizeof(uint32_t));
     obtain(c, st.point_list, R * sizeof(uint32_t));
-    st.sorting_size = (R * sizeof(uint32_t) + 127) / 128 * 128 + sort_temp_bytes(R);
+    st.sorting_size = (R * sizeof(uint32_t) + 127) / 128 * 128 + sort_temp_bytes(R) + expand_temp_bytes(R);
     obtain(c, st.list_sorting_space, st.sorting_size);
     if (b) *b = st;
     return (size_t)(c - chunk);
@@ -228,7 +229,12 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
     gsr_image_state_map(ichunk, W, H, &img);
 
     const int tile_bits = (int)gsr_get_higher_msb((uint32_t)tiles);  // GSCuda.cu:791-797: end_bit = 32 + this
-    const int tile_passes = sort_num_passes(tile_bits);
+    // tile half of the sort: bin expansion (bin_expand.cu) unless asked otherwise or the grid has too many bins
+    const int bins_x = (gx + BIN_SIDE - 1) >> BIN_SHIFT, bins_y = (gy + BIN_SIDE - 1) >> BIN_SHIFT;
+    const int nbins = bins_x * bins_y;
+    const bool bin_mode = !(a->flags & GSR_FLAG_RADIX_BINNING) && nbins <= MAX_BINS;
+    const int bin_bits = (int)gsr_get_higher_msb((uint32_t)nbins);
+    const int tile_passes = sort_num_passes(bin_mode ? bin_bits : tile_bits);
     const int depth_passes = sort_num_passes(32);
     cudaEvent_t sort_ev[12];
     const bool sort_timed = tm.on;
@@ -249,7 +255,7 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         launches += rc;          \
     } while (0)
 
-    uint32_t R = 0;
+    uint32_t R = 0, Rc = 0;
     tm.mark();  // 0
     if (P > 0) {
         if ((rc = ensure_slot(slot)) < 0) GSR_FAIL(rc);
@@ -275,6 +281,7 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         pp.means2D = geom.means2D; pp.cov3D = geom.cov3D; pp.conic_opacity = geom.conic_opacity;
         pp.rgb = geom.rgb; pp.tiles_touched = geom.tiles_touched; pp.block_sums = geom.block_sums;
         pp.depth_keys = geom.depth_keys; pp.tile_rects = geom.tile_rects;
+        pp.coarse_block_sums = bin_mode ? geom.coarse_block_sums : nullptr;
         // all clears of the frame up front, so the kernels behind them form uninterrupted dependent-launch chains
         if (!sort32_prepare(geom.depth_sort_space, (size_t)P, 32, s)) GSR_FAIL(-(int)cudaGetLastError());
         {
@@ -284,7 +291,8 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         GSR_STAGE(launch_preprocess(pp, compat, s));
         tm.mark();  // 1
         const int nb = num_pre_blocks(P);
-        GSR_STAGE(launch_scan_block_sums(geom.block_sums, nb, geom.block_sums + nb, slot.dev, s));
+        GSR_STAGE(launch_scan_block_sums(geom.block_sums, nb, geom.block_sums + nb, slot.dev, s,
+                                         bin_mode ? geom.coarse_block_sums : nullptr));
         cudaError_t e = cudaEventRecord(slot.landed, s);
         if (e != cudaSuccess) GSR_FAIL(-(int)e);
         tm.mark();  // 2
@@ -300,14 +308,16 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         GSR_STAGE(launch_sort32(dp, s, sort_timed ? sort_ev : nullptr));
         // tile rects into depth order + scan of the per-block pair counts (same total, other order)
         GSR_STAGE(launch_gather_rects(P, geom.depth_sort_ids[1], geom.tile_rects, geom.sorted_rects,
-                                      geom.sorted_block_sums, geom.tiles_touched, geom.block_sums, geom.point_offsets, s));
+                                      geom.sorted_block_sums, geom.tiles_touched, geom.block_sums, geom.point_offsets,
+                                      bin_mode, s));
         const int ndb = num_dup_blocks(P);
         GSR_STAGE(launch_scan_block_sums(geom.sorted_block_sums, ndb, geom.sorted_block_sums + ndb, nullptr, s));
         tm.mark();  // 3
         // the one host round trip: num_rendered decides the binning allocation (GSCuda.cu:772,782)
         e = cudaEventSynchronize(slot.landed);
         if (e != cudaSuccess) GSR_FAIL(-(int)e);
-        R = *static_cast<volatile uint32_t*>(slot.host);
+        R = static_cast<volatile uint32_t*>(slot.host)[0];
+        Rc = bin_mode ? static_cast<volatile uint32_t*>(slot.host)[1] : 0u;
     } else {
         tm.mark();
         tm.mark();
@@ -341,27 +351,63 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
                         reinterpret_cast<uint32_t*>(bin.point_list_keys_unsorted) + R};
     uint32_t* v32[2] = {bin.point_list_unsorted, reinterpret_cast<uint32_t*>(bin.list_sorting_space)};
     char* tile_temp = bin.list_sorting_space + ((size_t)R * sizeof(uint32_t) + 127) / 128 * 128;
-    uint32_t* tile_hist = sort32_prepare(tile_temp, (size_t)R, tile_bits, s);
-    if (!tile_hist) GSR_FAIL(-(int)cudaGetLastError());
-    GSR_STAGE(launch_duplicate_sorted(P, gx, geom.depth_sort_ids[1], geom.sorted_rects, geom.sorted_block_sums, k32[0],
-                                      v32[0], tile_hist, tile_bits, s));
-    tm.mark();  // 4
-    {
-        Sort32Plan tp;
-        memset(&tp, 0, sizeof(tp));
-        tp.n = (size_t)R; tp.end_bit = tile_bits;
-        tp.keys_in = k32[0]; tp.vals_in = v32[0];
-        tp.kbuf[0] = k32[1]; tp.kbuf[1] = k32[0];
-        tp.vbuf[0] = v32[1]; tp.vbuf[1] = v32[0];
-        tp.keys_out = nullptr; tp.vals_out = bin.point_list;
-        tp.expand_low = reinterpret_cast<const uint32_t*>(geom.depths);  // key = tile << 32 | depth bits
-        tp.keys_out64 = bin.point_list_keys;
-        tp.temp = tile_temp; tp.hist_ready = true;
-        GSR_STAGE(launch_sort32(tp, s, sort_timed ? sort_ev + 6 : nullptr));
+    if (bin_mode) {
+        // (Gaussian, bin) records in depth order -> stable sort by bin id -> expansion of every bin into the
+        // sorted per-tile lists and the tile ranges (bin_expand.cu)
+        if (Rc == 0 || Rc > R) GSR_FAIL(GSR_ERR_INVALID_ARG);  // cannot happen: every pair lies in one of its Gaussian's bins
+        uint32_t* bin_hist = sort32_prepare(tile_temp, (size_t)Rc, bin_bits, s);
+        if (!bin_hist) GSR_FAIL(-(int)cudaGetLastError());
+        GSR_STAGE(launch_duplicate_sorted(P, bins_x, geom.depth_sort_ids[1], geom.sorted_rects, geom.sorted_block_sums,
+                                          k32[0], v32[0], bin_hist, bin_bits, s));
+        tm.mark();  // 4
+        const int out = tile_passes & 1;  // one pass: [0] -> [1]; two: [0] -> [1] -> [0]
+        {
+            Sort32Plan tp;
+            memset(&tp, 0, sizeof(tp));
+            tp.n = (size_t)Rc; tp.end_bit = bin_bits;
+            tp.keys_in = k32[0]; tp.vals_in = v32[0];
+            tp.kbuf[0] = k32[1]; tp.kbuf[1] = k32[0];
+            tp.vbuf[0] = v32[1]; tp.vbuf[1] = v32[0];
+            tp.keys_out = k32[out]; tp.vals_out = v32[out];
+            tp.temp = tile_temp; tp.hist_ready = true;
+            GSR_STAGE(launch_sort32(tp, s, sort_timed ? sort_ev + 6 : nullptr));
+        }
+        tm.mark();  // 5
+        ExpandPlan ep;
+        memset(&ep, 0, sizeof(ep));
+        ep.n_records = (size_t)Rc; ep.num_rendered = (size_t)R;
+        ep.rec_bins = k32[out]; ep.rec_ids = v32[out];
+        ep.tile_rects = geom.tile_rects; ep.depths = reinterpret_cast<const uint32_t*>(geom.depths);
+        ep.grid_x = gx; ep.grid_y = gy; ep.bins_x = bins_x; ep.bins_y = bins_y;
+        ep.temp = tile_temp + sort_temp_bytes((size_t)R);
+        ep.tile_counts = img.tile_order; ep.ranges = img.ranges;
+        ep.keys_out = bin.point_list_keys; ep.vals_out = bin.point_list;
+        ep.r1_quirk = compat && R == 1;
+        GSR_STAGE(launch_bin_expand(ep, s));
+        tm.mark();  // 6
+    } else {
+        uint32_t* tile_hist = sort32_prepare(tile_temp, (size_t)R, tile_bits, s);
+        if (!tile_hist) GSR_FAIL(-(int)cudaGetLastError());
+        GSR_STAGE(launch_duplicate_sorted(P, gx, geom.depth_sort_ids[1], geom.sorted_rects, geom.sorted_block_sums, k32[0],
+                                          v32[0], tile_hist, tile_bits, s));
+        tm.mark();  // 4
+        {
+            Sort32Plan tp;
+            memset(&tp, 0, sizeof(tp));
+            tp.n = (size_t)R; tp.end_bit = tile_bits;
+            tp.keys_in = k32[0]; tp.vals_in = v32[0];
+            tp.kbuf[0] = k32[1]; tp.kbuf[1] = k32[0];
+            tp.vbuf[0] = v32[1]; tp.vbuf[1] = v32[0];
+            tp.keys_out = nullptr; tp.vals_out = bin.point_list;
+            tp.expand_low = reinterpret_cast<const uint32_t*>(geom.depths);  // key = tile << 32 | depth bits
+            tp.keys_out64 = bin.point_list_keys;
+            tp.temp = tile_temp; tp.hist_ready = true;
+            GSR_STAGE(launch_sort32(tp, s, sort_timed ? sort_ev + 6 : nullptr));
+        }
+        tm.mark();  // 5
+        GSR_STAGE(launch_identify_ranges(bin.point_list_keys, R, img.ranges, tiles, compat, s, /*zero_first=*/false));
+        tm.mark();  // 6
     }
-    tm.mark();  // 5
-    GSR_STAGE(launch_identify_ranges(bin.point_list_keys, R, img.ranges, tiles, compat, s, /*zero_first=*/false));
-    tm.mark();  // 6
 
     BlendParams bp;
     memset(&bp, 0, sizeof(bp));
@@ -386,7 +432,10 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         t->depth_sort_ms = tm.ms(2, 3);
         t->duplicate_ms = tm.ms(3, 4);
         t->sort_ms = tm.ms(4, 5);
-        t->ranges_ms = tm.ms(5, 6);
+        t->ranges_ms = bin_mode ? 0.f : tm.ms(5, 6);
+        t->expand_ms = bin_mode ? tm.ms(5, 6) : 0.f;
+        t->num_coarse = (int)Rc;
+        t->binning_mode = bin_mode ? 0 : 1;
         t->blend_ms = tm.ms(6, 7);
         t->total_ms = tm.ms(0, 7);
         t->num_rendered = (int)R;

@@ -59,22 +59,26 @@ struct PreprocessParams {
     float* rgb;
     uint32_t* tiles_touched;
     uint32_t* block_sums;  // [ceil(P/256)]
+    uint32_t* coarse_block_sums;  // [ceil(P/256)] (Gaussian, bin) records of the block, or null
     uint32_t* depth_keys;  // [P] low half of the sort key: depth bits, 0xffffffff when nothing is emitted
     uint32_t* tile_rects;  // uint2[P]: (miny<<16|minx, height<<16|width) of the tile rect, 0 when nothing is emitted
 };
 
 // stage launchers (each returns the number of kernels it launched, or <0 on error)
 int launch_preprocess(const PreprocessParams& p, bool compat, cudaStream_t s);
+// sums2 (optional): a second per-block array that is only reduced; its total goes to total_host_mapped[1].
 int launch_scan_block_sums(uint32_t* block_sums, int num_blocks, uint32_t* total_dev, uint32_t* total_host_mapped,
-                           cudaStream_t s);
+                           cudaStream_t s, const uint32_t* sums2 = nullptr);
 // Duplication blocks take num_dup_blocks(P) groups of consecutive depth ranks.
 int num_dup_blocks(int P);
 // sorted_rects[i] = tile_rects[sorted_ids[i]] and block_sums[b] = pairs emitted by the depth ranks of block b.
 // Also materialises point_offsets[i] = inclusive scan of tiles_touched in index order (GSCuda.cu:771) from
 // block_offsets = the exclusive offsets of preprocess' 256-Gaussian blocks.
+// coarse: sorted_rects receives the rect in units of 8x8-tile bins (same packing) and block_sums the number of
+// (Gaussian, bin) records — the input of the bin-expansion path.
 int launch_gather_rects(int P, const uint32_t* sorted_ids, const uint32_t* tile_rects, uint32_t* sorted_rects,
                         uint32_t* block_sums, const uint32_t* tiles_touched, const uint32_t* block_offsets,
-                        uint32_t* point_offsets, cudaStream_t s);
+                        uint32_t* point_offsets, bool coarse, cudaStream_t s);
 // Emits the (tile, Gaussian) pairs of the Gaussians taken in depth order: 32-bit tile keys + Gaussian
 // ids, and accumulates the tile-digit histograms of the following radix passes into `hist`
 // ([passes][256], zeroed).  `block_offsets` = exclusive scan of launch_gather_rects' block_sums.
@@ -118,6 +122,39 @@ struct Sort32Plan {
 uint32_t* sort32_prepare(char* temp, size_t n, int end_bit, cudaStream_t s);
 // `events` (optional, passes+2 entries): before the histogram, after its scan, after every pass.
 int launch_sort32(const Sort32Plan& plan, cudaStream_t s, cudaEvent_t* events = nullptr);
+
+// ---- bin expansion (bin_expand.cu) -------------------------------------------------------------
+// Bins are 8x8 tiles.  The (Gaussian, bin) records, stably sorted by bin (so each bin lists its Gaussians in
+// depth order), are expanded into the per-tile sorted lists: point_list_keys / point_list / ranges.
+constexpr int BIN_SHIFT = 3;
+constexpr int BIN_SIDE = 1 << BIN_SHIFT;
+constexpr int BIN_TILES = BIN_SIDE * BIN_SIDE;  // 64: one bit per tile in a 64-bit mask
+constexpr int MAX_BINS = 4096;                  // larger grids fall back to radix passes over the pairs
+// the rect of tile_rects (miny<<16|minx, height<<16|width) in units of bins; empty stays empty
+__host__ __device__ __forceinline__ uint2 coarse_rect(const uint2 r) {
+    if (r.y == 0u) return make_uint2(0u, 0u);
+    const uint32_t x0 = r.x & 0xffffu, y0 = r.x >> 16, w = r.y & 0xffffu, h = r.y >> 16;
+    const uint32_t bx0 = x0 >> BIN_SHIFT, bx1 = (x0 + w - 1u) >> BIN_SHIFT;
+    const uint32_t by0 = y0 >> BIN_SHIFT, by1 = (y0 + h - 1u) >> BIN_SHIFT;
+    return make_uint2((by0 << 16) | bx0, ((by1 - by0 + 1u) << 16) | (bx1 - bx0 + 1u));
+}
+size_t expand_temp_bytes(size_t R);
+struct ExpandPlan {
+    size_t n_records;             // (Gaussian, bin) records
+    size_t num_rendered;          // R
+    const uint32_t* rec_bins;     // [n_records] sorted bin ids
+    const uint32_t* rec_ids;      // [n_records] Gaussian ids, depth order inside each bin
+    const uint32_t* tile_rects;   // uint2[P]
+    const uint32_t* depths;       // [P] depth bits
+    int grid_x, grid_y, bins_x, bins_y;
+    char* temp;                   // expand_temp_bytes(R)
+    uint32_t* tile_counts;        // [tiles] scratch
+    uint32_t* ranges;             // uint2[tiles]
+    uint64_t* keys_out;           // [R]
+    uint32_t* vals_out;           // [R]
+    bool r1_quirk;                // GSRast-compat: a frame of exactly one pair never closes its range (GSCuda.cu:533-536)
+};
+int launch_bin_expand(const ExpandPlan& plan, cudaStream_t s);
 
 struct BlendParams {
     int W, H, grid_x, grid_y;

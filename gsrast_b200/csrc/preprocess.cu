@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(const Preproces
     __shared__ float s_cam[36];                       // view[16] proj[16] cam_pos[3]
     __shared__ float4 s_queue[PRE_THREADS / 32][32];  // per-warp survivors: dir.xyz, idx
     __shared__ uint32_t s_wsum[PRE_THREADS / 32];
+    __shared__ uint32_t s_wsum2[PRE_THREADS / 32];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -451,14 +452,18 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(const Preproces
     }
 
     // ---- per-block partial sum for the tiles_touched scan --------------------------------
+    // ... and of the (Gaussian, 8x8-tile bin) records the bin-expansion path will emit
+    const uint2 crec = coarse_rect(rec);
     const uint32_t wsum = __reduce_add_sync(0xffffffffu, tiles);
-    if (lane == 0) s_wsum[warp] = wsum;
+    const uint32_t wsum2 = __reduce_add_sync(0xffffffffu, (crec.y >> 16) * (crec.y & 0xffffu));
+    if (lane == 0) { s_wsum[warp] = wsum; s_wsum2[warp] = wsum2; }
     __syncthreads();
     if (tid == 0) {
-        uint32_t t = 0;
+        uint32_t t = 0, t2 = 0;
 #pragma unroll
-        for (int w = 0; w < PRE_THREADS / 32; ++w) t += s_wsum[w];
+        for (int w = 0; w < PRE_THREADS / 32; ++w) { t += s_wsum[w]; t2 += s_wsum2[w]; }
         p.block_sums[blockIdx.x] = t;
+        if (p.coarse_block_sums) p.coarse_block_sums[blockIdx.x] = t2;
     }
 }
 

@@ -35,6 +35,10 @@ typedef char* (*gsr_alloc_fn)(size_t bytes, void* user);
                                        T<0.001 termination, y-extent w/o sqrt, R==1 range quirk, stale image
                                        when nothing is rendered */
 #define GSR_FLAG_BLEND_SIMPLE 0x2u  /* use the plain per-tile blend kernel (no sub-tile culling); for A/B tests */
+#define GSR_FLAG_RADIX_BINNING 0x4u /* sort the tile half of the keys with radix passes over all num_rendered pairs
+                                       (the path CUB takes in the reference, GSCuda.cu:794-797) instead of the default
+                                       bin expansion (sort per 8x8-tile bin, expand each bin into its tiles); same
+                                       output bit for bit; also taken automatically for grids of more than 4096 bins */
 
 #define GSR_ERR_INVALID_ARG (-1000)
 #define GSR_ERR_ALLOC_FAILED (-1001)   /* an allocator callback returned NULL */
@@ -87,6 +91,12 @@ typedef struct gsr_stage_times {
                                then the tile-digit passes over the num_rendered pairs */
     float depth_sort_ms;    /* depth half of the LSD sort (P records), overlaps the num_rendered round trip */
     int depth_passes;
+    /* bin expansion (default binning mode): sort_ms then covers the bin-digit passes over the
+     * num_coarse (Gaussian, 8x8-tile bin) records, expand_ms the count / scan / fill kernels that turn
+     * each bin's depth-ordered list into the sorted per-tile lists and the tile ranges (ranges_ms = 0). */
+    float expand_ms;
+    int num_coarse;
+    int binning_mode;       /* 0 = bin expansion, 1 = radix passes over the pairs */
 } gsr_stage_times;
 
 /* Same call with explicit strides / flags (superset of the two above). */
@@ -148,13 +158,14 @@ typedef struct gsr_geometry_state {
     size_t depth_sort_size;
     uint32_t* sorted_rects;      /* [P][2] tile_rects gathered into depth order */
     uint32_t* sorted_block_sums; /* scan scratch of the pair counts in depth order (scan_size bytes) */
+    uint32_t* coarse_block_sums; /* per preprocess block: (Gaussian, 8x8-tile bin) records it will emit */
 } gsr_geometry_state;
 
 typedef struct gsr_image_state {
     uint32_t* ranges;     /* [tiles][2]  (start, end) into the sorted lists */
     uint32_t* n_contrib;  /* [W*H] */
     float* accum_alpha;   /* [W*H] final transmittance */
-    uint32_t* tile_order; /* [tiles] blend work order (heaviest tiles first) */
+    uint32_t* tile_order; /* [tiles] scratch: per-tile pair counts, then their exclusive scan (bin expansion) */
 } gsr_image_state;
 
 typedef struct gsr_binning_state {
@@ -162,7 +173,8 @@ typedef struct gsr_binning_state {
     uint64_t* point_list_keys;          /* [R] sorted (tile << 32 | depth bits) */
     uint32_t* point_list_unsorted;      /* [R] Gaussian ids in depth-ordered emission order */
     uint32_t* point_list;               /* [R] sorted Gaussian ids */
-    char* list_sorting_space;           /* second id ping-pong array [R] + histograms + look-back state */
+    char* list_sorting_space;           /* second id ping-pong array [R] + histograms + look-back state
+                                           + chunk tables of the bin expansion */
     size_t sorting_size;
 } gsr_binning_state;
 

@@ -20,16 +20,19 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("W,H,passes", [(128, 96, 1), (250, 130, 1), (1000, 555, 2), (4096, 4200, 3)])
 def test_tile_digit_pass_counts(oracle, W, H, passes):
-    """tiles <= 128 -> 1 tile-digit pass; 13-16 bits -> 2; > 65536 tiles -> 3."""
+    """Radix passes over the pairs (GSR_FLAG_RADIX_BINNING): tiles <= 128 -> 1 tile-digit pass;
+    13-16 bits -> 2; > 65536 tiles -> 3."""
+    from gsrast_b200 import _lib
     from gsrast_b200.rasterizer import get_higher_msb
 
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
     assert (get_higher_msb(tiles) + 7) // 8 == passes
     sc = S.make_config_scene("C1", P=12_345)[0]  # P deliberately not a multiple of 4 / 256 / 1024
     cam = Cm.default_camera(W, H)
-    cu = run_cuda(sc, cam, timings=True)
+    cu = run_cuda(sc, cam, timings=True, flags=_lib.FLAG_RADIX_BINNING)
     ref = run_oracle(oracle, sc, cam)
     assert_parity(cu, ref)
+    assert cu["times"]["binning_mode"] == 1
     assert cu["times"]["depth_passes"] == 4 and cu["times"]["sort_passes"] == 4 + passes
 
 

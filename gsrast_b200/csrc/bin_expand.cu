@@ -16,15 +16,15 @@
 //   1. every Gaussian is emitted once per 8x8-tile BIN its rect touches (~1.15 records per Gaussian
 //      at 1080p) and those records are radix-sorted by bin id (one 8-bit pass up to 256 bins) — each
 //      bin now lists its Gaussians in depth order;
-//   2. the record list of a bin is cut into chunks of 512; a chunk turns each record's rect into a
+//   2. the record list of a bin is cut into chunks of 256; a chunk turns each record's rect into a
 //      64-bit tile mask of the bin, and a 32x32 bit-matrix transpose across the lanes of a warp turns 32
 //      masks into 64 ballots (one per tile: which of the 32 records touch it).  popc of a ballot is a
 //      count, popc below the own lane is a stable rank;
 //   3. expand_count: per chunk and tile, pairs emitted; a scan over the chunks of a bin and over all
 //      tiles (row-major tile id) gives every (chunk, tile) its final offset and every tile its range —
 //      identifyTileRanges falls out of the scan, the sorted keys are never re-read;
-//   4. expand_fill: every chunk recomputes its ballots, ranks its pairs, stages them per tile in shared
-//      memory and writes 12 bytes per pair as contiguous runs straight into their final position.
+//   4. expand_fill: every chunk walks its ballots tile by tile (that IS the sorted order), stages the pairs
+//      in shared memory and writes 12 bytes per pair as contiguous runs straight into their final position.
 // Pair-level HBM traffic drops from 56 B/pair (8 written by the duplication, 2 x 16 by the first
 // pass, 8 + 4 + 12 by the last, 8 re-read for the ranges) to the 12 B/pair of the result itself.
 #include <algorithm>
@@ -37,22 +37,27 @@ namespace {
 
 constexpr int EXP_THREADS = 256;
 constexpr int EXP_WARPS = EXP_THREADS / 32;
-constexpr int EXP_CHUNK = 512;                 // records per chunk
-constexpr int EXP_WS = EXP_CHUNK / 32;         // warp-steps (32 records each) per chunk
-constexpr int EXP_PER_WARP = EXP_WS / EXP_WARPS;
-constexpr int EXP_CAP = 4096;                  // pairs staged per round (>= 32 * 64, the most one warp-step emits)
+constexpr int EXP_CHUNK = 256;                 // records per chunk: one per thread, one warp-step (32 records) per warp
+constexpr int EXP_WS = EXP_CHUNK / 32;         // warp-steps per chunk
+constexpr int EXP_CAP = 2048;                  // pairs staged per round (>= 32 * 64, the most one warp-step emits)
+constexpr int EXP_QUARTERS = EXP_THREADS / BIN_TILES;   // fill: thread = (tile, quarter of the warp-steps)
+constexpr int EXP_WS_PER_Q = EXP_WS / EXP_QUARTERS;
 constexpr int TABLE_THREADS = 1024;
+constexpr int SCAN_PARTS = EXP_THREADS / BIN_TILES;     // chunk scan: thread = (tile, part of the bin's chunks)
 
 __host__ __device__ inline size_t align128(size_t v) { return (v + 127) / 128 * 128; }
 
 struct ExpandTemp {
     uint32_t* bin_start;        // [MAX_BINS + 1] first record of every bin (+ n_records)
     uint32_t* bin_chunk_first;  // [MAX_BINS + 1] first chunk of every bin (+ number of chunks)
+    uint32_t* done_counter;     // [1] bins whose chunk scan has finished (the last one scans the tiles)
     uint4* chunk_desc;          // [max_chunks] bin, first record, end record, -
     uint32_t* chunk_counts;     // [max_chunks][64] pairs per tile, then exclusive prefix over the bin's chunks
+    uint32_t* chunk_ballots;    // [max_chunks][EXP_WS][64] per warp-step and tile: which of the 32 records touch it
+    uint2* rec_data;            // [R] per record: Gaussian id, depth bits (gathered once, by the count pass)
 };
 
-size_t max_chunks(size_t R) { return R / EXP_CHUNK + MAX_BINS + 1; }
+size_t max_chunks(size_t R) { return R / EXP_CHUNK + std::min<size_t>((size_t)MAX_BINS, R) + 1; }
 
 ExpandTemp carve(char* temp, size_t R) {
     ExpandTemp t;
@@ -61,15 +66,22 @@ ExpandTemp carve(char* temp, size_t R) {
     c += align128((MAX_BINS + 1) * sizeof(uint32_t));
     t.bin_chunk_first = reinterpret_cast<uint32_t*>(c);
     c += align128((MAX_BINS + 1) * sizeof(uint32_t));
+    t.done_counter = reinterpret_cast<uint32_t*>(c);
+    c += 128;
     t.chunk_desc = reinterpret_cast<uint4*>(c);
     c += align128(max_chunks(R) * sizeof(uint4));
     t.chunk_counts = reinterpret_cast<uint32_t*>(c);
+    c += align128(max_chunks(R) * BIN_TILES * sizeof(uint32_t));
+    t.chunk_ballots = reinterpret_cast<uint32_t*>(c);
+    c += align128(max_chunks(R) * EXP_WS * BIN_TILES * sizeof(uint32_t));
+    t.rec_data = reinterpret_cast<uint2*>(c);
     return t;
 }
 
 // ---- bin boundaries -----------------------------------------------------------------------------
 // One warp per bin b in [0, nbins]: bin_start[b] = first record whose bin id is >= b (32-ary search
-// in the sorted bin ids: 5 round trips for 2^25 records instead of 25).
+// in the sorted bin ids: 5 round trips for 2^25 records instead of 25).  Only needed when the bin ids
+// took more than one radix pass; with a single pass the digit histogram IS the per-bin count.
 __global__ void __launch_bounds__(EXP_THREADS) bin_bounds_kernel(const uint32_t* __restrict__ rec_bins, const uint32_t n,
                                                                   const int nbins, uint32_t* __restrict__ bin_start) {
     const int lane = threadIdx.x & 31;
@@ -98,34 +110,16 @@ __global__ void __launch_bounds__(EXP_THREADS) bin_bounds_kernel(const uint32_t*
     if (lane == 0) bin_start[b] = lo;
 }
 
-// ---- chunk table --------------------------------------------------------------------------------
-// One CTA: chunks per bin, their exclusive scan, and one descriptor per chunk.
-__global__ void __launch_bounds__(TABLE_THREADS) chunk_table_kernel(const int nbins, const uint32_t* __restrict__ bin_start,
-                                                                    uint32_t* __restrict__ bin_chunk_first,
-                                                                    uint4* __restrict__ chunk_desc) {
-    constexpr int PER = MAX_BINS / TABLE_THREADS;  // 4 consecutive bins per thread
-    __shared__ uint32_t s_warp[TABLE_THREADS / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    gsr_pdl_wait();
-    gsr_pdl_launch_dependents();
-    uint32_t st[PER + 1], nch[PER], tsum = 0;
-#pragma unroll
-    for (int j = 0; j <= PER; ++j) {
-        const int b = tid * PER + j;
-        st[j] = (b <= nbins) ? bin_start[b] : 0u;
-    }
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-        const int b = tid * PER + j;
-        nch[j] = (b < nbins) ? (st[j + 1] - st[j] + EXP_CHUNK - 1) / EXP_CHUNK : 0u;
-        tsum += nch[j];
-    }
-    uint32_t incl = tsum;
+// exclusive scan of one value per thread over a TABLE_THREADS-wide CTA; returns the exclusive prefix
+__device__ __forceinline__ uint32_t table_scan(const uint32_t v, uint32_t* s_warp, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += t;
     }
+    __syncthreads();  // s_warp may still be read from a previous call
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
     if (warp == 0) {
@@ -137,21 +131,87 @@ __global__ void __launch_bounds__(TABLE_THREADS) chunk_table_kernel(const int nb
             if (lane >= d) wi += t;
         }
         s_warp[lane] = wi - w;
+        if (lane == 31) s_warp[32] = wi;
     }
     __syncthreads();
-    uint32_t run = s_warp[warp] + incl - tsum;
+    if (total) *total = s_warp[32];
+    return s_warp[warp] + incl - v;
+}
+
+// ---- chunk table --------------------------------------------------------------------------------
+// One CTA: per-bin record ranges (from the single-pass digit histogram `bin_counts`, or from bin_start
+// when the bin ids took two passes), chunks per bin, their exclusive scan, one descriptor per chunk.
+__global__ void __launch_bounds__(TABLE_THREADS) chunk_table_kernel(const int nbins, const uint32_t* __restrict__ bin_counts,
+                                                                    uint32_t* __restrict__ bin_start,
+                                                                    uint32_t* __restrict__ bin_chunk_first,
+                                                                    uint4* __restrict__ chunk_desc,
+                                                                    uint32_t* __restrict__ done_counter) {
+    constexpr int PER = MAX_BINS / TABLE_THREADS;  // 4 consecutive bins per thread
+    __shared__ uint32_t s_warp[33];
+    __shared__ uint32_t s_start[MAX_BINS + 1];
+    __shared__ uint32_t s_first[MAX_BINS + 1];
+    const int tid = threadIdx.x;
+    gsr_pdl_wait();
+    gsr_pdl_launch_dependents();
+    if (tid == 0) *done_counter = 0;
+    uint32_t cnt[PER], st[PER + 1], nch[PER], tsum = 0;
+    if (bin_counts) {
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int b = tid * PER + j;
+            cnt[j] = (b < nbins) ? __ldg(bin_counts + b) : 0u;
+            tsum += cnt[j];
+        }
+        uint32_t run = table_scan(tsum, s_warp, nullptr);
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            st[j] = run;
+            run += cnt[j];
+        }
+        st[PER] = run;
+    } else {
+#pragma unroll
+        for (int j = 0; j <= PER; ++j) {
+            const int b = tid * PER + j;
+            st[j] = (b <= nbins) ? bin_start[b] : 0u;
+        }
+    }
+    tsum = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        const int b = tid * PER + j;
+        nch[j] = (b < nbins) ? (st[j + 1] - st[j] + EXP_CHUNK - 1) / EXP_CHUNK : 0u;
+        tsum += nch[j];
+    }
+    uint32_t total = 0;
+    uint32_t run = table_scan(tsum, s_warp, &total);
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
         const int b = tid * PER + j;
         if (b < nbins) {
+            s_start[b] = st[j];
+            s_first[b] = run;
             bin_chunk_first[b] = run;
-            for (uint32_t k = 0; k < nch[j]; ++k) {
-                const uint32_t s0 = st[j] + k * EXP_CHUNK;
-                chunk_desc[run + k] = make_uint4((uint32_t)b, s0, min(s0 + (uint32_t)EXP_CHUNK, st[j + 1]), 0u);
-            }
+            if (bin_counts) bin_start[b] = st[j];
             run += nch[j];
+            if (b == nbins - 1) {
+                s_start[nbins] = st[j + 1];
+                s_first[nbins] = run;
+                bin_chunk_first[nbins] = run;  // number of chunks
+                if (bin_counts) bin_start[nbins] = st[j + 1];
+            }
         }
-        if (b == nbins - 1) bin_chunk_first[nbins] = run;  // total number of chunks
+    }
+    __syncthreads();
+    // descriptors, one chunk per thread and round: bin by binary search over the first-chunk table
+    for (uint32_t k = tid; k < total; k += TABLE_THREADS) {
+        int lo = 0, hi = nbins - 1;  // largest b with s_first[b] <= k (empty bins share their successor's value)
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_first[mid] <= k) lo = mid; else hi = mid - 1;
+        }
+        const uint32_t s0 = s_start[lo] + (k - s_first[lo]) * EXP_CHUNK;
+        chunk_desc[k] = make_uint4((uint32_t)lo, s0, min(s0 + (uint32_t)EXP_CHUNK, s_start[lo + 1]), 0u);
     }
 }
 
@@ -170,13 +230,18 @@ __device__ __forceinline__ uint64_t bin_mask(const uint2 rec, const int bx8, con
 }
 
 // 32x32 bit-matrix transpose across a warp: lane i holds row i, afterwards lane j holds column j
-// (bit i of the result = bit j of lane i's input).  Five butterfly stages, one shuffle each.
+// (bit i of the result = bit j of lane i's input).  Five butterfly stages, one shuffle each: at stage j a
+// lane keeps the half of every 2j-bit group that stays (`keep`) and takes the other half, shifted by j,
+// from lane ^ j.
 __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, const int lane) {
     uint32_t m = 0x0000ffffu;
 #pragma unroll
     for (int j = 16; j >= 1; j >>= 1) {
         const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
-        x = (lane & j) ? (((y >> j) & m) | (x & ~m)) : ((x & m) | ((y & m) << j));
+        const bool up = (lane & j) != 0;
+        const uint32_t keep = up ? ~m : m;
+        const uint32_t t = up ? (y >> j) : (y << j);
+        x = (x & keep) | (t & ~keep);
         m ^= m << (j >> 1);
     }
     return x;
@@ -187,6 +252,8 @@ struct ExpandArgs {
     const uint4* chunk_desc;
     const uint32_t* num_chunks;  // device: bin_chunk_first[nbins]
     uint32_t* chunk_counts;
+    uint32_t* chunk_ballots;
+    uint2* rec_data;
     const uint2* tile_rects;
     const uint32_t* depths;
     const uint32_t* tile_start;  // [tiles] exclusive scan of the per-tile totals
@@ -195,7 +262,10 @@ struct ExpandArgs {
     int grid_x, grid_y, bins_x;
 };
 
-// ---- pass 1: pairs per (chunk, tile) ----------------------------------------------------------------
+// ---- pass 1: ballots and pairs per (chunk, tile) --------------------------------------------------------
+// Thread i of chunk c owns record i: gathers its tile rect and depth bits (the only random accesses of the
+// expansion), builds the tile mask of the bin; every warp transposes its 32 masks into 64 ballots.  Left for
+// the fill pass: the ballots, (id, depth) per record, and the chunk's pairs per tile.
 __global__ void __launch_bounds__(EXP_THREADS) expand_count_kernel(const ExpandArgs a) {
     __shared__ uint32_t s_cnt[BIN_TILES];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -207,127 +277,160 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_count_kernel(const ExpandA
     if (tid < BIN_TILES) s_cnt[tid] = 0;
     __syncthreads();
     const int bx8 = (int)(d.x % (uint32_t)a.bins_x) << BIN_SHIFT, by8 = (int)(d.x / (uint32_t)a.bins_x) << BIN_SHIFT;
-    uint64_t m[EXP_PER_WARP];
-#pragma unroll
-    for (int k = 0; k < EXP_PER_WARP; ++k) {
-        const uint32_t r = d.y + (uint32_t)((warp + k * EXP_WARPS) * 32 + lane);
-        m[k] = 0ull;
-        if (r < d.z) m[k] = bin_mask(__ldg(a.tile_rects + __ldg(a.rec_ids + r)), bx8, by8);
+    const uint32_t r = d.y + (uint32_t)tid;
+    uint64_t m = 0ull;
+    if (r < d.z) {
+        const uint32_t id = __ldg(a.rec_ids + r);
+        const uint2 rect = __ldg(a.tile_rects + id);
+        const uint32_t dep = __ldg(a.depths + id);
+        m = bin_mask(rect, bx8, by8);
+        a.rec_data[r] = make_uint2(id, dep);
     }
-    uint32_t c_lo = 0, c_hi = 0;
-#pragma unroll
-    for (int k = 0; k < EXP_PER_WARP; ++k) {
-        if (d.y + (uint32_t)((warp + k * EXP_WARPS) * 32) < d.z) {  // warp-uniform
-            c_lo += __popc(warp_transpose32((uint32_t)m[k], lane));
-            c_hi += __popc(warp_transpose32((uint32_t)(m[k] >> 32), lane));
-        }
-    }
-    if (c_lo) atomicAdd(&s_cnt[lane], c_lo);
-    if (c_hi) atomicAdd(&s_cnt[32 + lane], c_hi);
+    const uint32_t bl = warp_transpose32((uint32_t)m, lane);
+    const uint32_t bh = warp_transpose32((uint32_t)(m >> 32), lane);
+    uint32_t* bal = a.chunk_ballots + ((size_t)c * EXP_WS + warp) * BIN_TILES;
+    bal[lane] = bl;
+    bal[32 + lane] = bh;
+    if (bl) atomicAdd(&s_cnt[lane], (uint32_t)__popc(bl));
+    if (bh) atomicAdd(&s_cnt[32 + lane], (uint32_t)__popc(bh));
     __syncthreads();
     if (tid < BIN_TILES) a.chunk_counts[(size_t)c * BIN_TILES + tid] = s_cnt[tid];
 }
 
-// ---- scan 1: over the chunks of every bin, per tile ---------------------------------------------------
-// One CTA of 64 threads per bin; thread t walks the bin's chunks: counts -> exclusive prefix (in place),
-// total -> tile_counts[tile id].  Every tile of the grid belongs to exactly one bin, so tile_counts is
-// written completely (no clear needed).
-__global__ void __launch_bounds__(BIN_TILES) expand_scan_chunks_kernel(const uint32_t* __restrict__ bin_chunk_first,
-                                                                       uint32_t* __restrict__ chunk_counts,
-                                                                       uint32_t* __restrict__ tile_counts, const int grid_x,
-                                                                       const int grid_y, const int bins_x) {
-    const int t = threadIdx.x, b = blockIdx.x;
+// ---- scans: over the chunks of every bin per tile, then over the tiles -> ranges ---------------------------
+// One CTA per bin; thread = (tile t, part): the bin's chunks are split into SCAN_PARTS contiguous parts, each
+// summed (independent loads), combined through shared memory and rewritten as exclusive prefixes; the bin's
+// per-tile totals go to tile_counts[tile id].  Every tile of the grid belongs to exactly one bin, so
+// tile_counts is written completely.  The CTA that finishes last then scans tile_counts in row-major tile
+// order: tile_counts becomes the start of every tile's list and ranges[tile] = (start, start + count); a tile
+// nothing touches keeps (0, 0) exactly like the reference's cleared and never written entry (GSCuda.cu:800,
+// 504-538).
+__global__ void __launch_bounds__(EXP_THREADS) expand_scan_kernel(const uint32_t* __restrict__ bin_chunk_first,
+                                                                   uint32_t* __restrict__ chunk_counts,
+                                                                   uint32_t* tile_counts, const int grid_x,
+                                                                   const int grid_y, const int bins_x, const int nbins,
+                                                                   uint2* __restrict__ ranges, const int r1_quirk,
+                                                                   uint32_t* done_counter) {
+    __shared__ uint32_t s_part[SCAN_PARTS][BIN_TILES];
+    __shared__ uint32_t s_warp[EXP_WARPS];
+    __shared__ uint32_t s_carry;
+    __shared__ uint32_t s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t = tid & (BIN_TILES - 1), part = tid >> 6, b = blockIdx.x;
     gsr_pdl_wait();
     gsr_pdl_launch_dependents();
     const uint32_t first = __ldg(bin_chunk_first + b), last = __ldg(bin_chunk_first + b + 1);
-    uint32_t run = 0;
-    uint32_t* col = chunk_counts + (size_t)first * BIN_TILES + t;
-    uint32_t k = first;
-    for (; k + 4 <= last; k += 4, col += 4 * BIN_TILES) {
-        const uint32_t v0 = col[0], v1 = col[BIN_TILES], v2 = col[2 * BIN_TILES], v3 = col[3 * BIN_TILES];
-        col[0] = run; run += v0;
-        col[BIN_TILES] = run; run += v1;
-        col[2 * BIN_TILES] = run; run += v2;
-        col[3 * BIN_TILES] = run; run += v3;
+    const uint32_t n = last - first, per = (n + SCAN_PARTS - 1) / SCAN_PARTS;
+    const uint32_t k0 = first + min(n, (uint32_t)part * per), k1 = first + min(n, (uint32_t)(part + 1) * per);
+    uint32_t sum = 0;
+    {
+        const uint32_t* col = chunk_counts + (size_t)k0 * BIN_TILES + t;
+        uint32_t k = k0;
+        for (; k + 8 <= k1; k += 8, col += 8 * BIN_TILES) {
+            uint32_t v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = col[q * BIN_TILES];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sum += v[q];
+        }
+        for (; k < k1; ++k, col += BIN_TILES) sum += col[0];
     }
-    for (; k < last; ++k, col += BIN_TILES) {
-        const uint32_t v = col[0];
-        col[0] = run;
-        run += v;
-    }
-    const int tx = ((b % bins_x) << BIN_SHIFT) + (t & (BIN_SIDE - 1)), ty = ((b / bins_x) << BIN_SHIFT) + (t >> BIN_SHIFT);
-    if (tx < grid_x && ty < grid_y) tile_counts[ty * grid_x + tx] = run;
-}
-
-// ---- scan 2: over the tiles (row-major tile id) -> ranges ---------------------------------------------
-// One CTA.  tile_counts becomes its exclusive scan (the start of every tile's list) and ranges[tile] =
-// (start, start + count); a tile nothing touches keeps (0, 0) exactly like the reference's cleared and
-// never written entry (GSCuda.cu:800, 504-538).
-__global__ void __launch_bounds__(TABLE_THREADS) tile_ranges_kernel(uint32_t* __restrict__ tile_counts, const int tiles,
-                                                                    uint2* __restrict__ ranges, const int r1_quirk) {
-    constexpr int ITEMS = 8;
-    __shared__ uint32_t s_warp[TABLE_THREADS / 32];
-    __shared__ uint32_t s_carry;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_carry = 0;
-    gsr_pdl_wait();
-    gsr_pdl_launch_dependents();
+    s_part[part][t] = sum;
     __syncthreads();
-    for (int base = 0; base < tiles; base += TABLE_THREADS * ITEMS) {
+    uint32_t run = 0, total = 0;
+#pragma unroll
+    for (int q = 0; q < SCAN_PARTS; ++q) {
+        const uint32_t v = s_part[q][t];
+        if (q < part) run += v;
+        total += v;
+    }
+    {
+        uint32_t* col = chunk_counts + (size_t)k0 * BIN_TILES + t;
+        uint32_t k = k0;
+        for (; k + 4 <= k1; k += 4, col += 4 * BIN_TILES) {
+            const uint32_t v0 = col[0], v1 = col[BIN_TILES], v2 = col[2 * BIN_TILES], v3 = col[3 * BIN_TILES];
+            col[0] = run; run += v0;
+            col[BIN_TILES] = run; run += v1;
+            col[2 * BIN_TILES] = run; run += v2;
+            col[3 * BIN_TILES] = run; run += v3;
+        }
+        for (; k < k1; ++k, col += BIN_TILES) {
+            const uint32_t v = col[0];
+            col[0] = run;
+            run += v;
+        }
+    }
+    if (part == 0) {
+        const int tx = ((b % bins_x) << BIN_SHIFT) + (t & (BIN_SIDE - 1)), ty = ((b / bins_x) << BIN_SHIFT) + (t >> BIN_SHIFT);
+        if (tx < grid_x && ty < grid_y) tile_counts[ty * grid_x + tx] = total;
+    }
+    // ---- the last bin to finish scans the tiles ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(done_counter, 1u) == (uint32_t)(nbins - 1)) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    const int tiles = grid_x * grid_y;
+    constexpr int ITEMS = 8;
+    for (int base = 0; base < tiles; base += EXP_THREADS * ITEMS) {
         const int i0 = base + tid * ITEMS;
         uint32_t v[ITEMS], tsum = 0;
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
-            v[j] = (i0 + j < tiles) ? tile_counts[i0 + j] : 0u;
+            v[j] = (i0 + j < tiles) ? __ldcg(tile_counts + i0 + j) : 0u;
             tsum += v[j];
         }
         uint32_t incl = tsum;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const uint32_t x = __shfl_up_sync(0xffffffffu, incl, dd);
+            if (lane >= dd) incl += x;
         }
         if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
-        if (warp == 0) {
-            const uint32_t w = s_warp[lane];
-            uint32_t wi = w;
+        uint32_t woff = 0;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
-                if (lane >= d) wi += t;
-            }
-            s_warp[lane] = wi - w;
-        }
-        __syncthreads();
-        uint32_t run = s_carry + s_warp[warp] + incl - tsum;
+        for (int w = 0; w < EXP_WARPS; ++w)
+            if (w < warp) woff += s_warp[w];
+        uint32_t r = s_carry + woff + incl - tsum;
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
             if (i0 + j < tiles) {
-                tile_counts[i0 + j] = run;
+                tile_counts[i0 + j] = r;
                 // GSRast-compat with a single pair in the frame: .x = 0 is written, .y never is (GSCuda.cu:533-536)
-                ranges[i0 + j] = (v[j] && !r1_quirk) ? make_uint2(run, run + v[j]) : make_uint2(0u, 0u);
+                ranges[i0 + j] = (v[j] && !r1_quirk) ? make_uint2(r, r + v[j]) : make_uint2(0u, 0u);
             }
-            run += v[j];
+            r += v[j];
         }
         __syncthreads();
-        if (tid == TABLE_THREADS - 1) s_carry = run;
+        if (tid == EXP_THREADS - 1) s_carry = r;
         __syncthreads();
     }
 }
 
 // ---- pass 2: rank, stage, write ------------------------------------------------------------------------
-__global__ void __launch_bounds__(EXP_THREADS, 4) expand_fill_kernel(const ExpandArgs a) {
+// Thread = (tile t of the bin, quarter q of the chunk's warp-steps).  The pairs of tile t are the set bits of
+// its ballots, warp-step by warp-step, lane by lane — exactly the order of the sorted list — so a thread walks
+// its ballots and appends (id, depth) records to the tile's run in the staging buffer; the buffer is then
+// written out as one contiguous run per tile.  Chunks that emit more than EXP_CAP pairs take several rounds of
+// whole warp-steps.
+__global__ void __launch_bounds__(EXP_THREADS) expand_fill_kernel(const ExpandArgs a) {
     __shared__ uint32_t s_bal[EXP_WS][BIN_TILES];      // ballot of tile t in warp-step ws
     __shared__ uint32_t s_pre[EXP_WS + 1][BIN_TILES];  // pairs of tile t before warp-step ws; [EXP_WS] = chunk total
-    __shared__ uint32_t s_wstot[EXP_WS + 1];           // pairs before warp-step ws (all tiles)
+    __shared__ uint32_t s_wspart[2][EXP_WS];           // pairs of warp-step ws, tiles 0-31 / 32-63
+    __shared__ uint32_t s_round[EXP_WS + 1];           // round r covers warp-steps [s_round[r], s_round[r+1])
+    __shared__ uint32_t s_nrounds;
+    __shared__ uint32_t s_round_pairs;
     __shared__ uint32_t s_gbase[BIN_TILES];            // final position of the chunk's first pair of tile t
     __shared__ uint32_t s_tileid[BIN_TILES];
-    __shared__ uint32_t s_soff[BIN_TILES];             // per round: staged offset of tile t
+    __shared__ uint32_t s_soff[BIN_TILES];             // per round: staged offset of tile t (minus s_pre[ws_a][t])
     __shared__ uint32_t s_gadj[BIN_TILES];             // per round: final position = s_gadj[t] + staged index
-    __shared__ uint32_t s_id[EXP_CAP];
-    __shared__ uint32_t s_dep[EXP_CAP];
-    __shared__ unsigned char s_t[EXP_CAP];
+    __shared__ uint2 s_rec[EXP_CHUNK];                 // id, depth bits of the chunk's records
+    __shared__ uint2 s_out[EXP_CAP];                   // staged pairs: id, depth bits
+    __shared__ unsigned char s_t[EXP_CAP];             // staged pairs: tile of the bin
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     gsr_pdl_wait();
@@ -338,64 +441,59 @@ __global__ void __launch_bounds__(EXP_THREADS, 4) expand_fill_kernel(const Expan
     const int bx8 = (int)(d.x % (uint32_t)a.bins_x) << BIN_SHIFT, by8 = (int)(d.x / (uint32_t)a.bins_x) << BIN_SHIFT;
     const int nws = (int)((d.z - d.y + 31u) >> 5);
 
-    // 1. records of this thread: warp-steps warp and warp + 8
-    uint32_t id[EXP_PER_WARP], dep[EXP_PER_WARP];
-    uint64_t m[EXP_PER_WARP];
-#pragma unroll
-    for (int k = 0; k < EXP_PER_WARP; ++k) {
-        const uint32_t r = d.y + (uint32_t)((warp + k * EXP_WARPS) * 32 + lane);
-        id[k] = dep[k] = 0u;
-        m[k] = 0ull;
-        if (r < d.z) {
-            id[k] = __ldg(a.rec_ids + r);
-            m[k] = bin_mask(__ldg(a.tile_rects + id[k]), bx8, by8);
-            dep[k] = __ldg(a.depths + id[k]);
+    // 1. everything this chunk needs, all loads independent of each other
+    {
+        const uint32_t* bal = a.chunk_ballots + (size_t)c * EXP_WS * BIN_TILES;
+        const uint32_t b0 = __ldg(bal + tid), b1 = __ldg(bal + EXP_THREADS + tid);
+        const uint32_t r = d.y + (uint32_t)tid;
+        uint2 rec = make_uint2(0u, 0u);
+        if (r < d.z) rec = a.rec_data[r];
+        uint32_t gb = 0, tile = 0;
+        if (tid < BIN_TILES) {
+            const int tx = bx8 + (tid & (BIN_SIDE - 1)), ty = by8 + (tid >> BIN_SHIFT);
+            tile = (uint32_t)(ty * a.grid_x + tx);
+            if (tx < a.grid_x && ty < a.grid_y) gb = __ldg(a.tile_start + tile) + a.chunk_counts[(size_t)c * BIN_TILES + tid];
         }
-    }
-    // 2. ballots per tile and pairs per warp-step
-#pragma unroll
-    for (int k = 0; k < EXP_PER_WARP; ++k) {
-        const int ws = warp + k * EXP_WARPS;
-        const uint32_t bl = warp_transpose32((uint32_t)m[k], lane);
-        const uint32_t bh = warp_transpose32((uint32_t)(m[k] >> 32), lane);
-        s_bal[ws][lane] = bl;
-        s_bal[ws][32 + lane] = bh;
-        const uint32_t tot = __reduce_add_sync(0xffffffffu, (uint32_t)(__popc(bl) + __popc(bh)));
-        if (lane == 0) s_wstot[ws + 1] = tot;
+        (&s_bal[0][0])[tid] = b0;
+        (&s_bal[0][0])[EXP_THREADS + tid] = b1;
+        s_rec[tid] = rec;
+        if (tid < BIN_TILES) { s_gbase[tid] = gb; s_tileid[tid] = tile; }
     }
     __syncthreads();
-    // 3. per tile: prefix over the warp-steps, tile id, final base; prefix of the warp-step totals
+    // 2. per tile: prefix over the warp-steps; pairs per warp-step
     if (tid < BIN_TILES) {
         uint32_t run = 0;
 #pragma unroll
         for (int ws = 0; ws < EXP_WS; ++ws) {
+            const uint32_t n = (uint32_t)__popc(s_bal[ws][tid]);
             s_pre[ws][tid] = run;
-            run += __popc(s_bal[ws][tid]);
+            run += n;
+            const uint32_t tot = __reduce_add_sync(0xffffffffu, n);
+            if (lane == 0) s_wspart[warp][ws] = tot;
         }
         s_pre[EXP_WS][tid] = run;
-        const int tx = bx8 + (tid & (BIN_SIDE - 1)), ty = by8 + (tid >> BIN_SHIFT);
-        const bool inside = tx < a.grid_x && ty < a.grid_y;
-        const uint32_t tile = (uint32_t)(ty * a.grid_x + tx);
-        s_tileid[tid] = tile;
-        s_gbase[tid] = inside ? __ldg(a.tile_start + tile) + a.chunk_counts[(size_t)c * BIN_TILES + tid] : 0u;
-    } else if (tid == BIN_TILES) {
-        uint32_t run = 0;
-        s_wstot[0] = 0;
-#pragma unroll
-        for (int ws = 1; ws <= EXP_WS; ++ws) {
-            run += s_wstot[ws];
-            s_wstot[ws] = run;
-        }
     }
     __syncthreads();
-
-    // 4. rounds of at most EXP_CAP pairs: whole warp-steps [ws_a, ws_b)
-    const uint32_t lane_lt = (1u << lane) - 1u;
-    int ws_a = 0;
-    while (ws_a < nws) {
-        int ws_b = ws_a + 1;
-        while (ws_b < nws && s_wstot[ws_b + 1] - s_wstot[ws_a] <= (uint32_t)EXP_CAP) ++ws_b;
-        const uint32_t round_pairs = s_wstot[ws_b] - s_wstot[ws_a];
+    // 3. rounds of whole warp-steps, at most EXP_CAP pairs each (one thread; usually a single round)
+    if (tid == 0) {
+        uint32_t nr = 0, acc = 0;
+        s_round[0] = 0;
+        for (int ws = 0; ws < nws; ++ws) {
+            const uint32_t n = s_wspart[0][ws] + s_wspart[1][ws];
+            if (acc + n > (uint32_t)EXP_CAP) {
+                s_round[++nr] = (uint32_t)ws;
+                acc = 0;
+            }
+            acc += n;
+        }
+        s_round[++nr] = (uint32_t)nws;
+        s_nrounds = nr;
+    }
+    __syncthreads();
+    const int nrounds = (int)s_nrounds;
+    const int t = tid & (BIN_TILES - 1), q = tid >> 6;
+    for (int rd = 0; rd < nrounds; ++rd) {
+        const int ws_a = (int)s_round[rd], ws_b = (int)s_round[rd + 1];
         if (warp == 0) {
             // staged offsets: exclusive scan over the 64 tiles of the round's per-tile counts
             const uint32_t v0 = s_pre[ws_b][lane] - s_pre[ws_a][lane];
@@ -408,67 +506,75 @@ __global__ void __launch_bounds__(EXP_THREADS, 4) expand_fill_kernel(const Expan
                 if (lane >= dd) { i0 += t0; i1 += t1; }
             }
             const uint32_t tot0 = __shfl_sync(0xffffffffu, i0, 31);
+            const uint32_t tot1 = __shfl_sync(0xffffffffu, i1, 31);
             const uint32_t o0 = i0 - v0, o1 = tot0 + i1 - v1;
-            s_soff[lane] = o0 - s_pre[ws_a][lane];            // slot = s_soff[t] + s_pre[ws][t] + rank
+            s_soff[lane] = o0 - s_pre[ws_a][lane];            // slot = s_soff[t] + s_pre[ws][t] + rank in the ballot
             s_soff[32 + lane] = o1 - s_pre[ws_a][32 + lane];
             s_gadj[lane] = s_gbase[lane] + s_pre[ws_a][lane] - o0;
             s_gadj[32 + lane] = s_gbase[32 + lane] + s_pre[ws_a][32 + lane] - o1;
+            if (lane == 0) s_round_pairs = tot0 + tot1;
         }
         __syncthreads();
-#pragma unroll
-        for (int k = 0; k < EXP_PER_WARP; ++k) {
-            const int ws = warp + k * EXP_WARPS;
-            if (ws >= ws_a && ws < ws_b) {
-                uint64_t mm = m[k];
-                while (mm) {
-                    const int t = __ffsll((long long)mm) - 1;
-                    mm &= mm - 1ull;
-                    const uint32_t slot = s_soff[t] + s_pre[ws][t] + __popc(s_bal[ws][t] & lane_lt);
-                    s_id[slot] = id[k];
-                    s_dep[slot] = dep[k];
-                    s_t[slot] = (unsigned char)t;
+        const uint32_t round_pairs = s_round_pairs;
+        {
+            const int w0 = max(ws_a, q * EXP_WS_PER_Q), w1 = min(ws_b, (q + 1) * EXP_WS_PER_Q);
+            if (w0 < w1) {
+                uint32_t slot = s_soff[t] + s_pre[w0][t];
+                for (int ws = w0; ws < w1; ++ws) {
+                    uint32_t bits = s_bal[ws][t];
+                    while (bits) {
+                        const int l = __ffs((int)bits) - 1;
+                        bits &= bits - 1u;
+                        s_out[slot] = s_rec[ws * 32 + l];
+                        s_t[slot] = (unsigned char)t;
+                        ++slot;
+                    }
                 }
             }
         }
         __syncthreads();
         for (uint32_t j = tid; j < round_pairs; j += EXP_THREADS) {
-            const int t = s_t[j];
-            const uint32_t g = s_gadj[t] + j;
-            a.keys_out[g] = ((uint64_t)s_tileid[t] << 32) | (uint64_t)s_dep[j];  // GSCuda.cu:466-471
-            a.vals_out[g] = s_id[j];
+            const int tt = s_t[j];
+            const uint32_t g = s_gadj[tt] + j;
+            const uint2 o = s_out[j];
+            a.keys_out[g] = ((uint64_t)s_tileid[tt] << 32) | (uint64_t)o.y;  // GSCuda.cu:466-471
+            a.vals_out[g] = o.x;
         }
         __syncthreads();
-        ws_a = ws_b;
     }
 }
 
 }  // namespace
 
 size_t expand_temp_bytes(size_t R) {
-    return 128 + 2 * align128((MAX_BINS + 1) * sizeof(uint32_t)) + align128(max_chunks(R) * sizeof(uint4)) +
-           align128(max_chunks(R) * BIN_TILES * sizeof(uint32_t));
+    return 256 + 2 * align128((MAX_BINS + 1) * sizeof(uint32_t)) + align128(max_chunks(R) * sizeof(uint4)) +
+           align128(max_chunks(R) * BIN_TILES * sizeof(uint32_t)) +
+           align128(max_chunks(R) * EXP_WS * BIN_TILES * sizeof(uint32_t)) + align128(R * sizeof(uint2));
 }
 
 int launch_bin_expand(const ExpandPlan& p, cudaStream_t s) {
     const int nbins = p.bins_x * p.bins_y;
-    const int tiles = p.grid_x * p.grid_y;
     if (nbins < 1 || nbins > MAX_BINS || p.n_records == 0 || p.n_records > p.num_rendered) return GSR_ERR_INVALID_ARG;
     if (p.n_records >= ((size_t)1 << 31)) return GSR_ERR_TOO_MANY_PAIRS;
     ExpandTemp t = carve(p.temp, p.num_rendered);
     const unsigned nchunk_bound =
         (unsigned)(p.n_records / EXP_CHUNK + std::min<size_t>((size_t)nbins, p.n_records) + 1);  // <= max_chunks(R)
     int launches = 0;
-    GSR_CUDA_TRY(launch_pdl(bin_bounds_kernel, dim3((nbins + 1 + EXP_WARPS - 1) / EXP_WARPS), dim3(EXP_THREADS), 0, s,
-                            p.rec_bins, (uint32_t)p.n_records, nbins, t.bin_start));
-    ++launches;
-    GSR_CUDA_TRY(launch_pdl(chunk_table_kernel, dim3(1), dim3(TABLE_THREADS), 0, s, nbins, (const uint32_t*)t.bin_start,
-                            t.bin_chunk_first, t.chunk_desc));
+    if (!p.bin_counts) {
+        GSR_CUDA_TRY(launch_pdl(bin_bounds_kernel, dim3((nbins + 1 + EXP_WARPS - 1) / EXP_WARPS), dim3(EXP_THREADS), 0, s,
+                                p.rec_bins, (uint32_t)p.n_records, nbins, t.bin_start));
+        ++launches;
+    }
+    GSR_CUDA_TRY(launch_pdl(chunk_table_kernel, dim3(1), dim3(TABLE_THREADS), 0, s, nbins, p.bin_counts, t.bin_start,
+                            t.bin_chunk_first, t.chunk_desc, t.done_counter));
     ++launches;
     ExpandArgs a;
     a.rec_ids = p.rec_ids;
     a.chunk_desc = t.chunk_desc;
     a.num_chunks = t.bin_chunk_first + nbins;
     a.chunk_counts = t.chunk_counts;
+    a.chunk_ballots = t.chunk_ballots;
+    a.rec_data = t.rec_data;
     a.tile_rects = reinterpret_cast<const uint2*>(p.tile_rects);
     a.depths = p.depths;
     a.tile_start = p.tile_counts;
@@ -477,12 +583,9 @@ int launch_bin_expand(const ExpandPlan& p, cudaStream_t s) {
     a.grid_x = p.grid_x; a.grid_y = p.grid_y; a.bins_x = p.bins_x;
     GSR_CUDA_TRY(launch_pdl(expand_count_kernel, dim3(nchunk_bound), dim3(EXP_THREADS), 0, s, a));
     ++launches;
-    GSR_CUDA_TRY(launch_pdl(expand_scan_chunks_kernel, dim3(nbins), dim3(BIN_TILES), 0, s,
-                            (const uint32_t*)t.bin_chunk_first, t.chunk_counts, p.tile_counts, p.grid_x, p.grid_y,
-                            p.bins_x));
-    ++launches;
-    GSR_CUDA_TRY(launch_pdl(tile_ranges_kernel, dim3(1), dim3(TABLE_THREADS), 0, s, p.tile_counts, tiles,
-                            reinterpret_cast<uint2*>(p.ranges), p.r1_quirk ? 1 : 0));
+    GSR_CUDA_TRY(launch_pdl(expand_scan_kernel, dim3(nbins), dim3(EXP_THREADS), 0, s, (const uint32_t*)t.bin_chunk_first,
+                            t.chunk_counts, p.tile_counts, p.grid_x, p.grid_y, p.bins_x, nbins,
+                            reinterpret_cast<uint2*>(p.ranges), p.r1_quirk ? 1 : 0, t.done_counter));
     ++launches;
     GSR_CUDA_TRY(launch_pdl(expand_fill_kernel, dim3(nchunk_bound), dim3(EXP_THREADS), 0, s, a));
     ++launches;

@@ -377,6 +377,7 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         memset(&ep, 0, sizeof(ep));
         ep.n_records = (size_t)Rc; ep.num_rendered = (size_t)R;
         ep.rec_bins = k32[out]; ep.rec_ids = v32[out];
+        ep.bin_counts = tile_passes == 1 ? bin_hist : nullptr;  // single pass: the digit histogram is the bin histogram
         ep.tile_rects = geom.tile_rects; ep.depths = reinterpret_cast<const uint32_t*>(geom.depths);
         ep.grid_x = gx; ep.grid_y = gy; ep.bins_x = bins_x; ep.bins_y = bins_y;
         ep.temp = tile_temp + sort_temp_bytes((size_t)R);

@@ -144,6 +144,7 @@ struct ExpandPlan {
     size_t num_rendered;          // R
     const uint32_t* rec_bins;     // [n_records] sorted bin ids
     const uint32_t* rec_ids;      // [n_records] Gaussian ids, depth order inside each bin
+    const uint32_t* bin_counts;   // [nbins] records per bin (the digit histogram of a single-pass sort), or null
     const uint32_t* tile_rects;   // uint2[P]
     const uint32_t* depths;       // [P] depth bits
     int grid_x, grid_y, bins_x, bins_y;

@@ -127,18 +127,21 @@ __global__ void __launch_bounds__(PRE_THREADS) gather_rects_kernel(const int P, 
                                                                    uint32_t* __restrict__ block_sums,
                                                                    const uint32_t* __restrict__ tiles_touched,
                                                                    const uint32_t* __restrict__ block_offsets,
-                                                                   uint32_t* __restrict__ point_offsets) {
+                                                                   uint32_t* __restrict__ point_offsets,
+                                                                   const uint32_t* __restrict__ n_sorted) {
     __shared__ uint32_t s_warp[PRE_THREADS / 32];
     __shared__ uint32_t s_pw[PRE_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     gsr_pdl_wait();
     gsr_pdl_launch_dependents();
+    // the depth sort drops the Gaussians that emit nothing: only the first Pn depth ranks exist
+    const int Pn = n_sorted ? min(P, (int)__ldg(n_sorted)) : P;
     // (a)
     uint32_t cnt = 0;
 #pragma unroll
     for (int c = 0; c < DUP_GPT; ++c) {
         const int i = blockIdx.x * DUP_GAUSS + c * PRE_THREADS + tid;
-        if (i < P) {
+        if (i < Pn) {
             // the tile rect preprocess computed with getRect (GSCuda.cu:237-259; duplicateWithKeys recomputes
             // the same rect, :445-458).  Gaussians that emit nothing (radii <= 0, :440-443) carry an empty rect.
             uint2 rec = __ldg(tile_rects + __ldg(sorted_ids + i));
@@ -202,9 +205,9 @@ __global__ void __launch_bounds__(PRE_THREADS) gather_rects_kernel(const int P, 
 // thread.  The digit histograms of the tile passes are counted here (shared-memory atomics, flushed once
 // per block), so the sort never re-reads the keys.
 __global__ void __launch_bounds__(PRE_THREADS) duplicate_sorted_kernel(
-    const int P, const int grid_x, const uint32_t* __restrict__ sorted_ids, const uint2* __restrict__ sorted_rects,
+    const int P_all, const int grid_x, const uint32_t* __restrict__ sorted_ids, const uint2* __restrict__ sorted_rects,
     const uint32_t* __restrict__ block_offsets, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-    uint32_t* __restrict__ hist, const int tile_bits) {
+    uint32_t* __restrict__ hist, const int tile_bits, const uint32_t* __restrict__ n_sorted) {
     __shared__ uint32_t s_excl[DUP_GAUSS + 1];
     __shared__ uint32_t s_warp[PRE_THREADS / 32];
     __shared__ uint32_t s_gid[DUP_GAUSS];
@@ -219,6 +222,8 @@ __global__ void __launch_bounds__(PRE_THREADS) duplicate_sorted_kernel(
     const int i0 = blockIdx.x * DUP_GAUSS + DUP_GPT * tid;
     gsr_pdl_wait();
     gsr_pdl_launch_dependents();
+    const int P = n_sorted ? min(P_all, (int)__ldg(n_sorted)) : P_all;  // depth ranks that exist
+    if (blockIdx.x * DUP_GAUSS >= P) return;
     // every global load of the block is issued here, before anything waits
     const uint32_t boff = __ldg(block_offsets + blockIdx.x);
     uint2 rec[DUP_GPT];
@@ -397,28 +402,28 @@ int num_dup_blocks(int P) { return ((P > 0 ? P : 0) + DUP_GAUSS - 1) / DUP_GAUSS
 
 int launch_gather_rects(int P, const uint32_t* sorted_ids, const uint32_t* tile_rects, uint32_t* sorted_rects,
                         uint32_t* block_sums, const uint32_t* tiles_touched, const uint32_t* block_offsets,
-                        uint32_t* point_offsets, bool coarse, cudaStream_t s) {
+                        uint32_t* point_offsets, bool coarse, cudaStream_t s, const uint32_t* n_sorted) {
     if (P <= 0) return 0;
     const int blocks = num_dup_blocks(P);
     cudaError_t e =
         coarse ? launch_pdl(gather_rects_kernel<true>, dim3(blocks), dim3(PRE_THREADS), 0, s, P, sorted_ids,
                             reinterpret_cast<const uint2*>(tile_rects), reinterpret_cast<uint2*>(sorted_rects),
-                            block_sums, tiles_touched, block_offsets, point_offsets)
+                            block_sums, tiles_touched, block_offsets, point_offsets, n_sorted)
                : launch_pdl(gather_rects_kernel<false>, dim3(blocks), dim3(PRE_THREADS), 0, s, P, sorted_ids,
                             reinterpret_cast<const uint2*>(tile_rects), reinterpret_cast<uint2*>(sorted_rects),
-                            block_sums, tiles_touched, block_offsets, point_offsets);
+                            block_sums, tiles_touched, block_offsets, point_offsets, n_sorted);
     return e == cudaSuccess ? 1 : -(int)e;
 }
 
 int launch_duplicate_sorted(int P, int grid_x, const uint32_t* sorted_ids, const uint32_t* sorted_rects,
                             const uint32_t* block_offsets, uint32_t* keys32_out, uint32_t* vals_out, uint32_t* hist,
-                            int tile_bits, cudaStream_t s) {
+                            int tile_bits, cudaStream_t s, const uint32_t* n_sorted) {
     if (P <= 0) return 0;
     if (tile_bits < 1 || tile_bits > 32) return GSR_ERR_INVALID_ARG;
     const int blocks = num_dup_blocks(P);
     duplicate_sorted_kernel<<<blocks, PRE_THREADS, 0, s>>>(P, grid_x, sorted_ids,
                                                            reinterpret_cast<const uint2*>(sorted_rects), block_offsets,
-                                                           keys32_out, vals_out, hist, tile_bits);
+                                                           keys32_out, vals_out, hist, tile_bits, n_sorted);
     cudaError_t e = cudaPeekAtLastError();
     return e == cudaSuccess ? 1 : -(int)e;
 }

@@ -123,6 +123,22 @@ __device__ __forceinline__ float max_power_in_box(float a, float b, float c, flo
     return fmaxf(f1, f2);
 }
 
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 // Staged splat record: 48 bytes, three 16-byte shared loads off one base address.
 //   [0] x, y, a', b'      (conic pre-scaled by log2(e): power*log2(e) = a' dx^2 + c' dy^2 + b' dx dy)
 //   [1] c', opacity, r, g
@@ -133,7 +149,7 @@ __device__ __forceinline__ float max_power_in_box(float a, float b, float c, flo
 __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_kernel(const BlendParams p) {
     __shared__ float4 s_splat[BATCH * 3];
     __shared__ unsigned char s_mask[BATCH];                     // bit w: splat can reach warp w's 8x4 sub-rectangle
-    __shared__ unsigned char s_list[BLEND_THREADS / 32][BATCH]; // per warp: staged indices of its candidates
+    __shared__ unsigned short s_list[BLEND_THREADS / 32][BATCH]; // per warp: byte offsets (48 * staged index) of its candidates
 
     const int tile = p.tile_order ? (int)__ldg(p.tile_order + blockIdx.x) : (int)blockIdx.x;
     const int tile_x = tile % p.grid_x, tile_y = tile / p.grid_x;
@@ -145,7 +161,16 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
     const float pixf_x = (float)pix_x, pixf_y = (float)pix_y;
     const float tile_x0 = (float)(tile_x * TILE_X), tile_y0 = (float)(tile_y * TILE_Y);
     const uint32_t lane_lt = (1u << lane) - 1u;
-    unsigned char* my_list = s_list[warp];
+    unsigned short* my_list = s_list[warp];
+    // 32-bit shared-window address of the staging buffer, formed once: the inner loop then issues plain
+    // LDS [reg + imm] (a generic float4* made the compiler re-derive the window base inside the loop)
+    uint32_t splat_base = (uint32_t)__cvta_generic_to_shared(s_splat);
+    uint32_t list_base = (uint32_t)__cvta_generic_to_shared(my_list);
+    float t_min = p.t_min;
+    // opaque to the optimiser, so the three values live in registers instead of being re-materialised
+    // (S2UR SR_CgaCtaId + ULEA + LDCU) in every trip of the inner loop
+    float pixf_xo = pixf_x, pixf_yo = pixf_y;
+    asm volatile("" : "+r"(splat_base), "+r"(list_base), "+f"(t_min), "+f"(pixf_xo), "+f"(pixf_yo));
 
     gsr_pdl_wait();
     const uint2 range = reinterpret_cast<const uint2*>(p.ranges)[tile];
@@ -236,37 +261,38 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
             for (int c0 = 0; c0 < BATCH; c0 += 32) {
                 const bool mine = (s_mask[c0 + lane] >> warp) & 1u;
                 const unsigned bits = __ballot_sync(0xffffffffu, mine);
-                if (mine) my_list[n + __popc(bits & lane_lt)] = (unsigned char)(c0 + lane);
+                if (mine) my_list[n + __popc(bits & lane_lt)] = (unsigned short)((c0 + lane) * 48);
                 n += __popc(bits);
             }
             __syncwarp();
             // Branch-free inner loop.  A terminated pixel carries its final transmittance as a NEGATIVE T:
             // then w = alpha*T and T - w are negative, "T - w >= t_min" fails, nothing is blended, and
-            // no separate `done` flag has to be tested.  Per candidate: 2 LDS.128, 8 FP32 for the exponent,
-            // MUFU.EX2, 4 FP32 + 3 FSETP for alpha / transmittance, then predicated: LDS, 3 FFMA, T, last.
-            const uint32_t rbase = (uint32_t)(r * BATCH + 1);
+            // no separate `done` flag has to be tested.  Per candidate: LDS.U16, 2 LDS.128, 8 FP32 for the
+            // exponent, MUFU.EX2, 4 FP32 + 4 FSETP for alpha / transmittance, then predicated: LDS, 3 FFMA, T, last.
+            uint32_t last_off = 0xffffffffu;  // byte offset of the last splat blended in this batch
             for (int i0 = 0; i0 < n; i0 += 16) {
                 const int i1 = min(n, i0 + 16);
 #pragma unroll 2
                 for (int i = i0; i < i1; ++i) {
-                    const int j = my_list[i];
-                    const float4* sp = s_splat + 3 * j;
-                    const float4 a = sp[0];
-                    const float4 b = sp[1];
-                    const float dx = a.x - pixf_x, dy = a.y - pixf_y;
+                    const uint32_t off = lds16(list_base + 2u * (uint32_t)i);
+                    const float4 a = lds128(splat_base + off);
+                    const float4 b = lds128(splat_base + off + 16u);
+                    const float dx = a.x - pixf_xo, dy = a.y - pixf_yo;
+                    // the three terms are formed separately like the reference's (GSCuda.cu:634): a factored form
+                    // saves one FMUL but rounds differently where they cancel (elongated splats far from the centre)
                     const float p2 = fmaf(a.z, dx * dx, fmaf(b.x, dy * dy, a.w * (dx * dy)));
                     const float alpha = fminf(0.99f, b.y * ex2_approx(p2));
                     const float w = alpha * T;
                     const float test_T = T - w;  // T*(1-alpha)
                     const bool cand = (p2 <= 0.0f) && (alpha >= ALPHA_MIN);
-                    const bool ok = cand && (test_T >= p.t_min);
-                    const bool term = cand && !(test_T >= p.t_min);  // also true again later: idempotent below
+                    const bool ok = cand && (test_T >= t_min);
+                    const bool term = cand && !(test_T >= t_min);  // also true again later: idempotent below
                     if (ok) {
                         C0 = fmaf(b.z, w, C0);
                         C1 = fmaf(b.w, w, C1);
-                        C2 = fmaf(sp[2].x, w, C2);
+                        C2 = fmaf(lds32(splat_base + off + 32u), w, C2);
                         T = test_T;
-                        last = rbase + (uint32_t)j;
+                        last_off = off;
                     }
                     if (term) T = __uint_as_float(__float_as_uint(T) | 0x80000000u);  // T = -|T|: stop, keep final T
                 }
@@ -275,6 +301,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
                     break;
                 }
             }
+            if (last_off != 0xffffffffu) last = (uint32_t)(r * BATCH + 1) + last_off / 48u;
         }
     }
     T = fabsf(T);

@@ -256,6 +256,7 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
     } while (0)
 
     uint32_t R = 0, Rc = 0;
+    const uint32_t* n_depth = nullptr;  // device: Gaussians the depth sort kept
     tm.mark();  // 0
     if (P > 0) {
         if ((rc = ensure_slot(slot)) < 0) GSR_FAIL(rc);
@@ -305,11 +306,15 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         dp.vbuf[0] = geom.depth_sort_ids[0]; dp.vbuf[1] = geom.depth_sort_ids[1];
         dp.keys_out = geom.depth_sort_keys[1]; dp.vals_out = geom.depth_sort_ids[1];
         dp.temp = geom.depth_sort_space; dp.hist_ready = false;
+        // Gaussians that emit nothing carry the key 0xffffffff (preprocess): the sort drops them, so its later
+        // passes, the rect gather and the duplication only see the n_depth <= P Gaussians that are on screen
+        dp.drop_pad = true;
+        n_depth = sort32_kept_count(geom.depth_sort_space, (size_t)P, 32);
         GSR_STAGE(launch_sort32(dp, s, sort_timed ? sort_ev : nullptr));
         // tile rects into depth order + scan of the per-block pair counts (same total, other order)
         GSR_STAGE(launch_gather_rects(P, geom.depth_sort_ids[1], geom.tile_rects, geom.sorted_rects,
                                       geom.sorted_block_sums, geom.tiles_touched, geom.block_sums, geom.point_offsets,
-                                      bin_mode, s));
+                                      bin_mode, s, n_depth));
         const int ndb = num_dup_blocks(P);
         GSR_STAGE(launch_scan_block_sums(geom.sorted_block_sums, ndb, geom.sorted_block_sums + ndb, nullptr, s));
         tm.mark();  // 3
@@ -358,7 +363,7 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         uint32_t* bin_hist = sort32_prepare(tile_temp, (size_t)Rc, bin_bits, s);
         if (!bin_hist) GSR_FAIL(-(int)cudaGetLastError());
         GSR_STAGE(launch_duplicate_sorted(P, bins_x, geom.depth_sort_ids[1], geom.sorted_rects, geom.sorted_block_sums,
-                                          k32[0], v32[0], bin_hist, bin_bits, s));
+                                          k32[0], v32[0], bin_hist, bin_bits, s, n_depth));
         tm.mark();  // 4
         const int out = tile_passes & 1;  // one pass: [0] -> [1]; two: [0] -> [1] -> [0]
         {
@@ -390,7 +395,7 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         uint32_t* tile_hist = sort32_prepare(tile_temp, (size_t)R, tile_bits, s);
         if (!tile_hist) GSR_FAIL(-(int)cudaGetLastError());
         GSR_STAGE(launch_duplicate_sorted(P, gx, geom.depth_sort_ids[1], geom.sorted_rects, geom.sorted_block_sums, k32[0],
-                                          v32[0], tile_hist, tile_bits, s));
+                                          v32[0], tile_hist, tile_bits, s, n_depth));
         tm.mark();  // 4
         {
             Sort32Plan tp;

@@ -76,15 +76,16 @@ int num_dup_blocks(int P);
 // block_offsets = the exclusive offsets of preprocess' 256-Gaussian blocks.
 // coarse: sorted_rects receives the rect in units of 8x8-tile bins (same packing) and block_sums the number of
 // (Gaussian, bin) records — the input of the bin-expansion path.
+// n_sorted (device, optional): only the first *n_sorted entries of sorted_ids are defined (sort32 with drop_pad).
 int launch_gather_rects(int P, const uint32_t* sorted_ids, const uint32_t* tile_rects, uint32_t* sorted_rects,
                         uint32_t* block_sums, const uint32_t* tiles_touched, const uint32_t* block_offsets,
-                        uint32_t* point_offsets, bool coarse, cudaStream_t s);
+                        uint32_t* point_offsets, bool coarse, cudaStream_t s, const uint32_t* n_sorted = nullptr);
 // Emits the (tile, Gaussian) pairs of the Gaussians taken in depth order: 32-bit tile keys + Gaussian
 // ids, and accumulates the tile-digit histograms of the following radix passes into `hist`
 // ([passes][256], zeroed).  `block_offsets` = exclusive scan of launch_gather_rects' block_sums.
 int launch_duplicate_sorted(int P, int grid_x, const uint32_t* sorted_ids, const uint32_t* sorted_rects,
                             const uint32_t* block_offsets, uint32_t* keys32_out, uint32_t* vals_out, uint32_t* hist,
-                            int tile_bits, cudaStream_t s);
+                            int tile_bits, cudaStream_t s, const uint32_t* n_sorted = nullptr);
 // zero_first: clear ranges[num_tiles] here (otherwise the caller has already done it)
 int launch_identify_ranges(const uint64_t* keys, size_t n, uint32_t* ranges, int num_tiles, bool compat,
                            cudaStream_t s, bool zero_first = true);
@@ -116,7 +117,13 @@ struct Sort32Plan {
     uint64_t* keys_out64;
     char* temp;       // sort_temp_bytes(n), prepared by sort32_prepare
     bool hist_ready;  // the producer of keys_in already accumulated the digit histograms
+    // Keys equal to 0xffffffff are dropped: the histogram does not count them, the first pass compacts them away,
+    // the later passes and every consumer work on the first sort32_kept_count() entries of the output only
+    // (the rest of the output arrays is undefined).  Needs >= 2 passes and !hist_ready.
+    bool drop_pad;
 };
+// Device word that holds the number of kept keys after launch_sort32 with drop_pad (same temp, n, end_bit).
+const uint32_t* sort32_kept_count(char* temp, size_t n, int end_bit);
 // Zeroes the histograms / tickets / look-back state in `temp`; returns the histogram array
 // ([pass][256]) for producers that count digits themselves, or nullptr on error.
 uint32_t* sort32_prepare(char* temp, size_t n, int end_bit, cudaStream_t s);

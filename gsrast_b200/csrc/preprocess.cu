@@ -72,12 +72,13 @@ constexpr float SH_C3_0 = -0.5900435899266435f, SH_C3_1 = 2.890611442640554f, SH
                 SH_C3_6 = -0.5900435899266435f;
 
 template <bool COMPAT>
-__global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(const PreprocessParams p, const int vec_means,
+__global__ void __launch_bounds__(PRE_THREADS, 6) preprocess_kernel(const PreprocessParams p, const int vec_means,
                                                                  const int vec_scales, const int vec_sh) {
     __shared__ __align__(16) float s_means[PRE_THREADS * 3];
     __shared__ __align__(16) float s_scales[PRE_THREADS * 3];
     __shared__ float s_cam[36];                       // view[16] proj[16] cam_pos[3]
-    __shared__ float4 s_queue[PRE_THREADS / 32][32];  // per-warp survivors: dir.xyz, idx
+    __shared__ int s_queue[PRE_THREADS / 32][32];     // per-warp survivors (Gaussian index), compacted
+    __shared__ float4 s_basis[PRE_THREADS / 32][32 * 4];  // their 16 SH basis factors (contract mode only)
     __shared__ uint32_t s_wsum[PRE_THREADS / 32];
     __shared__ uint32_t s_wsum2[PRE_THREADS / 32];
 
@@ -180,13 +181,17 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(const Preproces
 
         // The SH block of a Gaussian that passed the frustum test is needed ~200 instructions from now (after
         // the covariance math and the warp compaction): start pulling its two 128-byte lines into L2.
-        if (!COMPAT && alive && p.colors_precomp == nullptr) {
+        // Only for centres on or near the screen (a hint: an off-screen centre with a huge radius just misses).
+        if (!COMPAT && alive && p.colors_precomp == nullptr && fabsf(prx) < 1.25f && fabsf(pry) < 1.25f) {
             const char* shp = reinterpret_cast<const char*>(p.shs + (size_t)idx * p.M * 3);
             asm volatile("prefetch.global.L2 [%0];" ::"l"(shp));
             if (p.M * 12 > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(shp + 128));
         }
 
         float cov00 = 0.f, cov01 = 0.f, cov11 = 0.f;
+        float o_depth = 0.f;
+        float2 o_xy = make_float2(0.f, 0.f);
+        float4 o_conic = make_float4(0.f, 0.f, 0.f, 0.f);
         if (alive) {
             // ---- 3D covariance ---------------------------------------------------------
             float c[6];
@@ -327,9 +332,9 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(const Preproces
                 rec = make_uint2(((uint32_t)miny << 16) | (uint32_t)minx,
                                  ((uint32_t)(maxy - miny) << 16) | (uint32_t)(maxx - minx));
                 radius_out = ri;
-                p.depths[idx] = depth;
-                reinterpret_cast<float2*>(p.means2D)[idx] = make_float2(ix, iy);
-                reinterpret_cast<float4*>(p.conic_opacity)[idx] = make_float4(conx, cony, conz, __ldg(p.opacities + idx));
+                o_depth = depth;
+                o_xy = make_float2(ix, iy);
+                o_conic = make_float4(conx, cony, conz, __ldg(p.opacities + idx));
                 if (p.colors_precomp == nullptr) {
                     if (!COMPAT) {
                         need_sh = true;
@@ -346,6 +351,20 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(const Preproces
                 }
             }
         }
+        // depth / mean / conic are stored for EVERY Gaussian (zeros where nothing is emitted; the reference leaves
+        // those entries stale): whole sectors are written, so the memory system never has to read a sector back to
+        // merge a few surviving 4..16-byte records into it (measured: ~130 MB of DRAM reads per C2 frame)
+        p.depths[idx] = o_depth;
+        reinterpret_cast<float2*>(p.means2D)[idx] = o_xy;
+        reinterpret_cast<float4*>(p.conic_opacity)[idx] = o_conic;
+        if (tiles == 0 && p.colors_precomp == nullptr) {
+            float* o = p.rgb + (size_t)idx * 3;
+            o[0] = 0.f; o[1] = 0.f; o[2] = 0.f;
+            if (!COMPAT) {
+                unsigned char* cl = p.clamped + (size_t)idx * 3;
+                cl[0] = 0; cl[1] = 0; cl[2] = 0;
+            }
+        }
         p.radii[idx] = radius_out;
         p.tiles_touched[idx] = tiles;
         // low half of the sort key (GSCuda.cu:466-471); Gaussians that emit nothing sort last
@@ -354,30 +373,58 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(const Preproces
     }
 
     // ---- SH colour: 4 lanes per surviving Gaussian -----------------------------------------
+    // Phase 1 (owner thread, all lanes busy, no divergence): the 16 basis factors of the view direction go to
+    // shared memory.  Phase 2: lane (slot, q) owns coefficients 4q..4q+3 of survivor `slot` (3 coalesced float4
+    // = 48 contiguous bytes, 192 B per Gaussian across the 4 lanes), chains them with FMAs, and a two-step
+    // butterfly adds the four partial sums: rgb_c = ((s0 + s1) + (s2 + s3)) + 0.5 with
+    // s_q = fma(b3,c3, fma(b2,c2, fma(b1,c1, b0*c0))).  oracle/gsr_oracle.cpp evaluates the same tree.
     if (!COMPAT) {
         const unsigned mask = __ballot_sync(0xffffffffu, need_sh);
         if (mask) {
+            const int ncoef = min(p.M, (p.D + 1) * (p.D + 1));
+            float4* bp = s_basis[warp];
             if (need_sh) {
                 const int pos = __popc(mask & ((1u << lane) - 1u));
-                s_queue[warp][pos] = make_float4(dirx, diry, dirz, __int_as_float(idx));
+                s_queue[warp][pos] = idx;
+                const float x = dirx, y = diry, z = dirz;
+                const float xx = fmul(x, x), yy = fmul(y, y), zz = fmul(z, z);
+                const float xy = fmul(x, y), yz = fmul(y, z), xz = fmul(x, z);
+                float bf[16];
+                bf[0] = SH_C0;
+                bf[1] = -fmul(SH_C1, y);
+                bf[2] = fmul(SH_C1, z);
+                bf[3] = -fmul(SH_C1, x);
+                bf[4] = fmul(SH_C2_0, xy);
+                bf[5] = fmul(SH_C2_1, yz);
+                bf[6] = fmul(SH_C2_2, fsub(fsub(fmul(2.0f, zz), xx), yy));
+                bf[7] = fmul(SH_C2_3, xz);
+                bf[8] = fmul(SH_C2_4, fsub(xx, yy));
+                bf[9] = fmul(fmul(SH_C3_0, y), fsub(fmul(3.0f, xx), yy));
+                bf[10] = fmul(fmul(SH_C3_1, xy), z);
+                bf[11] = fmul(fmul(SH_C3_2, y), fsub(fsub(fmul(4.0f, zz), xx), yy));
+                bf[12] = fmul(fmul(SH_C3_3, z), fsub(fsub(fmul(2.0f, zz), fmul(3.0f, xx)), fmul(3.0f, yy)));
+                bf[13] = fmul(fmul(SH_C3_4, x), fsub(fsub(fmul(4.0f, zz), xx), yy));
+                bf[14] = fmul(fmul(SH_C3_5, z), fsub(xx, yy));
+                bf[15] = fmul(fmul(SH_C3_6, x), fsub(xx, fmul(3.0f, yy)));
+#pragma unroll
+                for (int k = 0; k < 16; ++k) bf[k] = (k < ncoef) ? bf[k] : 0.f;
+                // 64 B per survivor, float4 slots XOR-swizzled so that both these stores and the phase-2 loads
+                // are bank-conflict free
+                const int sw = (pos >> 1) & 3;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bp[pos * 4 + (j ^ sw)] = make_float4(bf[4 * j], bf[4 * j + 1], bf[4 * j + 2], bf[4 * j + 3]);
             }
             __syncwarp();
             const int n = __popc(mask);
             const int q = lane & 3;
-            const int ncoef = min(p.M, (p.D + 1) * (p.D + 1));
             const int nk = max(0, min(4, ncoef - 4 * q));  // coefficients this lane owns: 4q .. 4q+nk-1
             for (int r0 = 0; r0 < n; r0 += 8) {
                 const int slot = r0 + (lane >> 2);
                 const bool act = slot < n;
                 float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
                 int gidx = 0;
-                float t[4][3];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) t[k][0] = t[k][1] = t[k][2] = 0.f;
                 if (act) {
-                    const float4 e = s_queue[warp][slot];
-                    gidx = __float_as_int(e.w);
-                    const float x = e.x, y = e.y, z = e.z;
+                    gidx = s_queue[warp][slot];
                     float s[12];
                     const float* sp = p.shs + ((size_t)gidx * p.M + 4 * q) * 3;
                     if (nk == 4 && vec_sh) {
@@ -389,63 +436,21 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(const Preproces
 #pragma unroll
                         for (int i = 0; i < 12; ++i) s[i] = (i < nk * 3) ? __ldg(sp + i) : 0.f;
                     }
-                    const float xx = fmul(x, x), yy = fmul(y, y), zz = fmul(z, z);
-                    const float xy = fmul(x, y), yz = fmul(y, z), xz = fmul(x, z);
-                    float b0, b1, b2, b3;  // basis factor of each owned coefficient (sign folded in)
-                    if (q == 0) {
-                        b0 = SH_C0;
-                        b1 = -fmul(SH_C1, y);
-                        b2 = fmul(SH_C1, z);
-                        b3 = -fmul(SH_C1, x);
-                    } else if (q == 1) {
-                        b0 = fmul(SH_C2_0, xy);
-                        b1 = fmul(SH_C2_1, yz);
-                        b2 = fmul(SH_C2_2, fsub(fsub(fmul(2.0f, zz), xx), yy));
-                        b3 = fmul(SH_C2_3, xz);
-                    } else if (q == 2) {
-                        b0 = fmul(SH_C2_4, fsub(xx, yy));
-                        b1 = fmul(fmul(SH_C3_0, y), fsub(fmul(3.0f, xx), yy));
-                        b2 = fmul(fmul(SH_C3_1, xy), z);
-                        b3 = fmul(fmul(SH_C3_2, y), fsub(fsub(fmul(4.0f, zz), xx), yy));
-                    } else {
-                        b0 = fmul(fmul(SH_C3_3, z), fsub(fsub(fmul(2.0f, zz), fmul(3.0f, xx)), fmul(3.0f, yy)));
-                        b1 = fmul(fmul(SH_C3_4, x), fsub(fsub(fmul(4.0f, zz), xx), yy));
-                        b2 = fmul(fmul(SH_C3_5, z), fsub(xx, yy));
-                        b3 = fmul(fmul(SH_C3_6, x), fsub(xx, fmul(3.0f, yy)));
-                    }
-#pragma unroll
-                    for (int ch = 0; ch < 3; ++ch) {
-                        t[0][ch] = fmul(b0, s[ch]);
-                        t[1][ch] = fmul(b1, s[3 + ch]);
-                        t[2][ch] = fmul(b2, s[6 + ch]);
-                        t[3][ch] = fmul(b3, s[9 + ch]);
-                    }
+                    const float4 bq = bp[slot * 4 + (q ^ ((slot >> 1) & 3))];
+                    acc0 = __fmaf_rn(bq.w, s[9], __fmaf_rn(bq.z, s[6], __fmaf_rn(bq.y, s[3], fmul(bq.x, s[0]))));
+                    acc1 = __fmaf_rn(bq.w, s[10], __fmaf_rn(bq.z, s[7], __fmaf_rn(bq.y, s[4], fmul(bq.x, s[1]))));
+                    acc2 = __fmaf_rn(bq.w, s[11], __fmaf_rn(bq.z, s[8], __fmaf_rn(bq.y, s[5], fmul(bq.x, s[2]))));
                 }
-                // Chain the partial sums lane 0 -> 1 -> 2 -> 3 so the additions happen in the
-                // reference's coefficient order (bit-identical colours and clamp flags).
-#pragma unroll
-                for (int step = 0; step < 4; ++step) {
-                    const float p0 = __shfl_up_sync(0xffffffffu, acc0, 1);
-                    const float p1 = __shfl_up_sync(0xffffffffu, acc1, 1);
-                    const float p2 = __shfl_up_sync(0xffffffffu, acc2, 1);
-                    if (q == step) {
-                        if (step == 0) {
-                            acc0 = t[0][0]; acc1 = t[0][1]; acc2 = t[0][2];
-                        } else {
-                            acc0 = p0; acc1 = p1; acc2 = p2;
-                            if (nk > 0) { acc0 = fadd(acc0, t[0][0]); acc1 = fadd(acc1, t[0][1]); acc2 = fadd(acc2, t[0][2]); }
-                        }
-                        if (nk > 1) { acc0 = fadd(acc0, t[1][0]); acc1 = fadd(acc1, t[1][1]); acc2 = fadd(acc2, t[1][2]); }
-                        if (nk > 2) { acc0 = fadd(acc0, t[2][0]); acc1 = fadd(acc1, t[2][1]); acc2 = fadd(acc2, t[2][2]); }
-                        if (nk > 3) { acc0 = fadd(acc0, t[3][0]); acc1 = fadd(acc1, t[3][1]); acc2 = fadd(acc2, t[3][2]); }
-                    }
-                }
-                if (act && q == 3) {
-                    acc0 = fadd(acc0, 0.5f); acc1 = fadd(acc1, 0.5f); acc2 = fadd(acc2, 0.5f);
-                    unsigned char* cl = p.clamped + (size_t)gidx * 3;
-                    cl[0] = acc0 < 0.f; cl[1] = acc1 < 0.f; cl[2] = acc2 < 0.f;
-                    float* o = p.rgb + (size_t)gidx * 3;
-                    o[0] = fmaxf(acc0, 0.f); o[1] = fmaxf(acc1, 0.f); o[2] = fmaxf(acc2, 0.f);
+                acc0 = fadd(acc0, __shfl_xor_sync(0xffffffffu, acc0, 1));
+                acc1 = fadd(acc1, __shfl_xor_sync(0xffffffffu, acc1, 1));
+                acc2 = fadd(acc2, __shfl_xor_sync(0xffffffffu, acc2, 1));
+                acc0 = fadd(acc0, __shfl_xor_sync(0xffffffffu, acc0, 2));
+                acc1 = fadd(acc1, __shfl_xor_sync(0xffffffffu, acc1, 2));
+                acc2 = fadd(acc2, __shfl_xor_sync(0xffffffffu, acc2, 2));
+                if (act && q < 3) {  // lane q writes channel q: 12 contiguous bytes per Gaussian across 3 lanes
+                    const float v = fadd(q == 0 ? acc0 : (q == 1 ? acc1 : acc2), 0.5f);
+                    p.clamped[(size_t)gidx * 3 + q] = v < 0.f;
+                    p.rgb[(size_t)gidx * 3 + q] = fmaxf(v, 0.f);
                 }
             }
         }

@@ -30,6 +30,7 @@
 //      are handed out by an atomic ticket so a tile only ever waits for tiles that started;
 //   5. keys/values are written out from shared memory as contiguous per-digit runs.
 #include <algorithm>
+#include <atomic>
 
 #include "gsr_common.cuh"
 
@@ -79,6 +80,8 @@ __device__ __forceinline__ uint32_t digit_of(const uint32_t k, const int shift, 
 }
 __device__ __forceinline__ void pad_key(uint2& k) { k = make_uint2(~0u, ~0u); }
 __device__ __forceinline__ void pad_key(uint32_t& k) { k = ~0u; }
+__device__ __forceinline__ bool is_pad(const uint2 k) { return (k.x & k.y) == ~0u; }
+__device__ __forceinline__ bool is_pad(const uint32_t k) { return k == ~0u; }
 __device__ __forceinline__ uint32_t low_word(const uint2 k) { return k.x; }
 __device__ __forceinline__ uint32_t low_word(const uint32_t k) { return k; }
 
@@ -86,11 +89,17 @@ __device__ __forceinline__ uint32_t low_word(const uint32_t k) { return k; }
 // Block-shared counters updated with shared-memory atomics: measured on B200 (tools/microbench.cu)
 // at ~2.4 SM-cycles per warp-wide ATOMS against ~60 for match.any and ~25 for an 8-step ballot
 // match, so plain atomics are the right tool for an order-independent count.
+// kept != nullptr: keys equal to the all-ones pad value are NOT counted (the depth sort of the forward path drops
+// the Gaussians that emit nothing) and *kept receives the number of keys that were.
 template <typename KeyT, int PASSES>
 __global__ void __launch_bounds__(HIST_THREADS) histogram_kernel(const KeyT* __restrict__ keys, const size_t n,
-                                                                 const int end_bit, uint32_t* __restrict__ hist) {
+                                                                 const int end_bit, uint32_t* __restrict__ hist,
+                                                                 uint32_t* __restrict__ kept) {
     __shared__ uint32_t s_hist[PASSES * RADIX];
+    __shared__ uint32_t s_kept;
     const int tid = threadIdx.x;
+    if (tid == 0) s_kept = 0;
+    uint32_t my_kept = 0;
     for (int i = tid; i < PASSES * RADIX; i += HIST_THREADS) s_hist[i] = 0;
     gsr_pdl_wait();
     gsr_pdl_launch_dependents();
@@ -108,7 +117,8 @@ __global__ void __launch_bounds__(HIST_THREADS) histogram_kernel(const KeyT* __r
         }
 #pragma unroll
         for (int i = 0; i < PER_THREAD; ++i) {
-            if (base + (size_t)i * HIST_THREADS + tid < n) {
+            if (base + (size_t)i * HIST_THREADS + tid < n && !(kept && is_pad(k[i]))) {
+                ++my_kept;
 #pragma unroll
                 for (int ps = 0; ps < PASSES; ++ps) {
                     const int shift = ps * RADIX_BITS;
@@ -118,11 +128,16 @@ __global__ void __launch_bounds__(HIST_THREADS) histogram_kernel(const KeyT* __r
             }
         }
     }
+    if (kept) {
+        my_kept = __reduce_add_sync(0xffffffffu, my_kept);
+        if ((tid & 31) == 0 && my_kept) atomicAdd(&s_kept, my_kept);
+    }
     __syncthreads();
     for (int i = tid; i < PASSES * RADIX; i += HIST_THREADS) {
         const uint32_t c = s_hist[i];
         if (c) atomicAdd(hist + i, c);
     }
+    if (kept && tid == 0 && s_kept) atomicAdd(kept, s_kept);
 }
 
 // Status words carry flag and count in ONE 32-bit word, so relaxed gpu-scope accesses suffice.
@@ -145,6 +160,7 @@ struct PassArgs {
     void* keys_out;           // KeyT[n]; unused when expand_low != nullptr
     uint32_t* vals_out;
     size_t n;
+    const uint32_t* n_dev;    // non-null: the item count lives on the device (<= n); tiles past it exit at once
     int shift, nbits;
     const uint32_t* digit_counts;   // [RADIX] global digit histogram of this pass (every CTA scans it itself)
     uint32_t* status;               // [num_tiles][RADIX], zero-initialised
@@ -163,9 +179,12 @@ constexpr size_t onesweep_smem() {
     return (size_t)SORT_THREADS * SORT_ITEMS * (sizeof(KeyT) + 4) + (size_t)(2 * SORT_WARPS * RADIX + RADIX + 32) * 4;
 }
 
-template <typename KeyT, bool EXPAND, bool FULL, int SORT_ITEMS>
+// DROP: items whose key is the all-ones pad value are neither counted nor written (the output is compacted);
+// the tile then stages n_stage <= n_tile items.
+template <typename KeyT, bool EXPAND, bool FULL, int SORT_ITEMS, bool DROP>
 __device__ __forceinline__ void onesweep_tile(const PassArgs& a, const uint32_t n_tile, const uint32_t tile,
                                               unsigned char* s_raw) {
+    static_assert(!(DROP && FULL), "a dropping pass tests every item");
     constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
     KeyT* s_keys = reinterpret_cast<KeyT*>(s_raw);                                             // [SORT_TILE]
     uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_raw + (size_t)SORT_TILE * sizeof(KeyT));  // [SORT_TILE]
@@ -203,7 +222,9 @@ __device__ __forceinline__ void onesweep_tile(const PassArgs& a, const uint32_t 
     }
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; ++i) {
-        if (FULL || (warp_base + i * 32 + lane) < n_tile) atomicAdd(&my_hist[digit_of(key[i], shift, dmask)], 1u);
+        // out-of-range items carry the pad key, so in a dropping pass one test covers both
+        const bool ok = DROP ? !is_pad(key[i]) : (FULL || (warp_base + i * 32 + lane) < n_tile);
+        if (ok) atomicAdd(&my_hist[digit_of(key[i], shift, dmask)], 1u);
     }
     __syncthreads();
 
@@ -227,6 +248,7 @@ __device__ __forceinline__ void onesweep_tile(const PassArgs& a, const uint32_t 
     // exclusive scans over the digits: of the tile's counts, and of the global histogram (start of every
     // digit's output range) — two values through the same shuffles
     uint32_t block_off, digit_off;
+    uint32_t n_stage = n_tile;  // items this tile stages and writes
     {
         const uint32_t gcnt = a.digit_counts[tid];
         uint32_t incl = bins, gincl = gcnt;
@@ -238,10 +260,13 @@ __device__ __forceinline__ void onesweep_tile(const PassArgs& a, const uint32_t 
         }
         if (lane == 31) { s_misc[1 + warp] = incl; s_misc[1 + SORT_WARPS + warp] = gincl; }
         __syncthreads();
-        uint32_t off = 0, goff = 0;
+        uint32_t off = 0, goff = 0, tot = 0;
 #pragma unroll
-        for (int w = 0; w < SORT_WARPS; ++w)
+        for (int w = 0; w < SORT_WARPS; ++w) {
             if (w < warp) { off += s_misc[1 + w]; goff += s_misc[1 + SORT_WARPS + w]; }
+            tot += s_misc[1 + w];
+        }
+        if (DROP) n_stage = tot;
         block_off = off + incl - bins;
         digit_off = goff + gincl - gcnt;
     }
@@ -262,7 +287,7 @@ __device__ __forceinline__ void onesweep_tile(const PassArgs& a, const uint32_t 
     const uint32_t lane_lt = (1u << lane) - 1u;
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; ++i) {
-        const bool ok = FULL || (warp_base + i * 32 + lane) < n_tile;
+        const bool ok = DROP ? !is_pad(key[i]) : (FULL || (warp_base + i * 32 + lane) < n_tile);
         uint32_t* slot = my_hist + digit_of(key[i], shift, dmask);
         if (ok) atomicOr(slot + SORT_WARPS * RADIX, 1u << lane);
         __syncwarp();
@@ -371,12 +396,12 @@ __device__ __forceinline__ void onesweep_tile(const PassArgs& a, const uint32_t 
 #pragma unroll
         for (int k = 0; k < SORT_ITEMS; ++k) {
             const uint32_t j = tid + k * SORT_THREADS;
-            lo[k] = (FULL || j < n_tile) ? __ldg(a.expand_low + s_vals[j]) : 0u;
+            lo[k] = (FULL || j < n_stage) ? __ldg(a.expand_low + s_vals[j]) : 0u;
         }
 #pragma unroll
         for (int k = 0; k < SORT_ITEMS; ++k) {
             const uint32_t j = tid + k * SORT_THREADS;
-            if (FULL || j < n_tile) {
+            if (FULL || j < n_stage) {
                 const KeyT kk = s_keys[j];
                 const uint32_t g = s_global[digit_of(kk, shift, dmask)] + j;
                 a.keys_out64[g] = ((uint64_t)low_word(kk) << 32) | (uint64_t)lo[k];
@@ -388,7 +413,7 @@ __device__ __forceinline__ void onesweep_tile(const PassArgs& a, const uint32_t 
 #pragma unroll
         for (int k = 0; k < SORT_ITEMS; ++k) {
             const uint32_t j = tid + k * SORT_THREADS;
-            if (FULL || j < n_tile) {
+            if (FULL || j < n_stage) {
                 const KeyT kk = s_keys[j];
                 const uint32_t g = s_global[digit_of(kk, shift, dmask)] + j;
                 kout[g] = kk;
@@ -398,7 +423,7 @@ __device__ __forceinline__ void onesweep_tile(const PassArgs& a, const uint32_t 
     }
 }
 
-template <typename KeyT, bool EXPAND, int MIN_BLOCKS, int SORT_ITEMS>
+template <typename KeyT, bool EXPAND, int MIN_BLOCKS, int SORT_ITEMS, bool DROP = false>
 __global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) onesweep_kernel(const PassArgs a) {
     constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -415,11 +440,17 @@ __global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) onesweep_kernel(cons
     __syncthreads();
     const uint32_t tile = s_misc[0];
     const size_t tile_base = (size_t)tile * SORT_TILE;
-    const uint32_t n_tile = (uint32_t)min((size_t)SORT_TILE, a.n - tile_base);
-    if (n_tile == SORT_TILE)
-        onesweep_tile<KeyT, EXPAND, true, SORT_ITEMS>(a, n_tile, tile, s_raw);
+    // tickets are handed out in tile order and a tile only looks back, so the tiles past a device-side count
+    // can leave without publishing anything
+    const size_t n = a.n_dev ? min(a.n, (size_t)__ldg(a.n_dev)) : a.n;
+    if (tile_base >= n) return;
+    const uint32_t n_tile = (uint32_t)min((size_t)SORT_TILE, n - tile_base);
+    if (DROP)
+        onesweep_tile<KeyT, EXPAND, false, SORT_ITEMS, true>(a, n_tile, tile, s_raw);
+    else if (n_tile == SORT_TILE)
+        onesweep_tile<KeyT, EXPAND, true, SORT_ITEMS, false>(a, n_tile, tile, s_raw);
     else
-        onesweep_tile<KeyT, EXPAND, false, SORT_ITEMS>(a, n_tile, tile, s_raw);
+        onesweep_tile<KeyT, EXPAND, false, SORT_ITEMS, false>(a, n_tile, tile, s_raw);
 }
 
 size_t num_sort_tiles(size_t n, int items) { return (n + (size_t)SORT_THREADS * items - 1) / ((size_t)SORT_THREADS * items); }
@@ -450,13 +481,14 @@ TempLayout carve_temp(char* temp, size_t n, int passes, int items) {
 }
 
 template <typename KeyT>
-int launch_histogram(const KeyT* keys, size_t n, int end_bit, int passes, uint32_t* hist, cudaStream_t s) {
+int launch_histogram(const KeyT* keys, size_t n, int end_bit, int passes, uint32_t* hist, cudaStream_t s,
+                     uint32_t* kept = nullptr) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t per_block = (size_t)HIST_THREADS * 8;
     const unsigned hblocks = (unsigned)std::min<size_t>((n + per_block - 1) / per_block, (size_t)sms * 4);
-#define GSR_HIST(PS) launch_pdl(histogram_kernel<KeyT, PS>, dim3(hblocks), dim3(HIST_THREADS), 0, s, keys, n, end_bit, hist)
+#define GSR_HIST(PS) launch_pdl(histogram_kernel<KeyT, PS>, dim3(hblocks), dim3(HIST_THREADS), 0, s, keys, n, end_bit, hist, kept)
     switch (passes) {
         case 1: GSR_HIST(1); break;
         case 2: GSR_HIST(2); break;
@@ -471,14 +503,21 @@ int launch_histogram(const KeyT* keys, size_t n, int end_bit, int passes, uint32
     return 1;
 }
 
-template <typename KeyT, bool EXPAND, int MIN_BLOCKS, int ITEMS>
+template <typename KeyT, bool EXPAND, int MIN_BLOCKS, int ITEMS, bool DROP = false>
 int launch_pass(const PassArgs& a, cudaStream_t s) {
     constexpr size_t smem = onesweep_smem<KeyT, ITEMS>();
-    // per-device attribute; cheap enough to set on every call (one process may drive several GPUs)
-    GSR_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS, ITEMS>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GSR_CUDA_TRY(launch_pdl(onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS, ITEMS>, dim3((unsigned)num_sort_tiles(a.n, ITEMS)),
-                            dim3(SORT_THREADS), smem, s, a));
+    // per-device attribute (one process may drive several GPUs): set once per device and instantiation
+    static std::atomic<uint64_t> configured{0};
+    int dev = 0;
+    GSR_CUDA_TRY(cudaGetDevice(&dev));
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
+        GSR_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS, ITEMS, DROP>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured.fetch_or(bit, std::memory_order_release);
+    }
+    GSR_CUDA_TRY(launch_pdl(onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS, ITEMS, DROP>,
+                            dim3((unsigned)num_sort_tiles(a.n, ITEMS)), dim3(SORT_THREADS), smem, s, a));
     return 1;
 }
 
@@ -522,7 +561,7 @@ int launch_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint
     uint64_t* kout = keys_b; uint32_t* vout = vals_b;
     for (int ps = 0; ps < passes; ++ps) {
         PassArgs a;
-        a.keys_in = kin; a.vals_in = vin; a.keys_out = kout; a.vals_out = vout; a.n = n;
+        a.keys_in = kin; a.vals_in = vin; a.keys_out = kout; a.vals_out = vout; a.n = n; a.n_dev = nullptr;
         a.shift = ps * RADIX_BITS;
         a.nbits = std::min(RADIX_BITS, end_bit - a.shift);
         a.digit_counts = L.hist + ps * RADIX;
@@ -544,6 +583,10 @@ int launch_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint
 }
 
 // ---- 32-bit-key sort used by the forward path --------------------------------------------------
+const uint32_t* sort32_kept_count(char* temp, size_t n, int end_bit) {
+    return carve_temp(temp, n, sort_num_passes(end_bit), sort32_items(n)).tickets + MAX_PASSES + 1;
+}
+
 uint32_t* sort32_prepare(char* temp, size_t n, int end_bit, cudaStream_t s) {
     const int passes = sort_num_passes(end_bit);
     TempLayout L = carve_temp(temp, n, passes, sort32_items(n));
@@ -561,8 +604,10 @@ int launch_sort32(const Sort32Plan& p, cudaStream_t s, cudaEvent_t* events) {
     TempLayout L = carve_temp(p.temp, p.n, passes, items);
     int launches = 0;
     if (events) cudaEventRecord(events[0], s);
+    if (p.drop_pad && (p.hist_ready || passes < 2)) return GSR_ERR_INVALID_ARG;
+    uint32_t* kept = p.drop_pad ? L.tickets + MAX_PASSES + 1 : nullptr;
     if (!p.hist_ready) {
-        launches += launch_histogram<uint32_t>(p.keys_in, p.n, p.end_bit, passes, L.hist, s);
+        launches += launch_histogram<uint32_t>(p.keys_in, p.n, p.end_bit, passes, L.hist, s, kept);
     }
     if (events) cudaEventRecord(events[1], s);
     const uint32_t* kin = p.keys_in;
@@ -571,6 +616,7 @@ int launch_sort32(const Sort32Plan& p, cudaStream_t s, cudaEvent_t* events) {
         const bool last = ps == passes - 1;
         PassArgs a;
         a.keys_in = kin; a.vals_in = vin; a.n = p.n;
+        a.n_dev = (kept && ps > 0) ? kept : nullptr;  // the first pass compacts, the later ones see only what it kept
         a.shift = ps * RADIX_BITS;
         a.nbits = std::min(RADIX_BITS, p.end_bit - a.shift);
         a.digit_counts = L.hist + ps * RADIX;
@@ -580,7 +626,12 @@ int launch_sort32(const Sort32Plan& p, cudaStream_t s, cudaEvent_t* events) {
         a.error_flag = L.tickets + MAX_PASSES;
         a.expand_low = nullptr; a.keys_out64 = nullptr;
         int rc;
-        if (last) {
+        if (kept && ps == 0) {
+            a.keys_out = p.kbuf[0]; a.vals_out = p.vbuf[0];
+            rc = items == ITEMS_SMALL ? launch_pass<uint32_t, false, 6, ITEMS_SMALL, true>(a, s)
+                                      : launch_pass<uint32_t, false, GSR_MINB_LARGE, ITEMS_LARGE, true>(a, s);
+            kin = p.kbuf[0]; vin = p.vbuf[0];
+        } else if (last) {
             a.keys_out = p.keys_out; a.vals_out = p.vals_out;
             if (p.expand_low) {
                 a.expand_low = p.expand_low; a.keys_out64 = p.keys_out64;

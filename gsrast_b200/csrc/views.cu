@@ -20,7 +20,10 @@ namespace gsr {
 
 namespace {
 
-constexpr int LANES = 2;
+#ifndef GSR_LANES
+#define GSR_LANES 2
+#endif
+constexpr int LANES = GSR_LANES;
 constexpr int CAM_FLOATS = 36;  // view[16] proj[16] cam_pos[3] pad[1]
 
 struct Chunk {
@@ -47,7 +50,14 @@ struct Lane {
     HostSlot slot;
     float* cam_dev = nullptr;   // [CAM_FLOATS]
     float* cam_host = nullptr;  // pinned
-    float* frame_dev = nullptr; // [3*H*W], only for host-output rendering
+    // host-output rendering only: two frame buffers per lane, drained by the lane's own copy stream, so the
+    // lane renders its next view while the previous frame travels to the host
+    float* frame_dev[2] = {nullptr, nullptr};  // [3*H*W] each
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t rendered[2] = {nullptr, nullptr};
+    cudaEvent_t copied[2] = {nullptr, nullptr};
+    bool copy_pending[2] = {false, false};
+    int frame_ix = 0;
     int* rects = nullptr;       // [2*P], GSRast-compat only: the viewer always passes _rects (GSGaussians.cpp:137,204)
     cudaEvent_t cam_free = nullptr;  // cam_host may be overwritten once this fired
     cudaEvent_t done = nullptr;
@@ -86,7 +96,13 @@ void lane_destroy(Lane& l) {
     if (l.img.ptr) cudaFree(l.img.ptr);
     if (l.cam_dev) cudaFree(l.cam_dev);
     if (l.cam_host) cudaFreeHost(l.cam_host);
-    if (l.frame_dev) cudaFree(l.frame_dev);
+    if (l.copy_stream) cudaStreamSynchronize(l.copy_stream);
+    for (int b = 0; b < 2; ++b) {
+        if (l.frame_dev[b]) cudaFree(l.frame_dev[b]);
+        if (l.rendered[b]) cudaEventDestroy(l.rendered[b]);
+        if (l.copied[b]) cudaEventDestroy(l.copied[b]);
+    }
+    if (l.copy_stream) cudaStreamDestroy(l.copy_stream);
     if (l.rects) cudaFree(l.rects);
     if (l.cam_free) cudaEventDestroy(l.cam_free);
     if (l.done) cudaEventDestroy(l.done);
@@ -227,21 +243,41 @@ int gsr_renderer_render_host(void* h, const float* cameras, int n_views, float t
     Renderer* r = static_cast<Renderer*>(h);
     if (!r || !cameras || !out_color_host || n_views < 0) return GSR_ERR_INVALID_ARG;
     const size_t frame = (size_t)3 * r->W * r->H;
-    for (auto& l : r->lane)
-        if (!l.frame_dev) GSR_CUDA_TRY(cudaMalloc(&l.frame_dev, frame * sizeof(float)));
+    for (auto& l : r->lane) {
+        if (!l.copy_stream) GSR_CUDA_TRY(cudaStreamCreateWithFlags(&l.copy_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            if (!l.frame_dev[b]) GSR_CUDA_TRY(cudaMalloc(&l.frame_dev[b], frame * sizeof(float)));
+            if (!l.rendered[b]) GSR_CUDA_TRY(cudaEventCreateWithFlags(&l.rendered[b], cudaEventDisableTiming));
+            if (!l.copied[b]) GSR_CUDA_TRY(cudaEventCreateWithFlags(&l.copied[b], cudaEventDisableTiming));
+        }
+    }
     GSR_CUDA_TRY(cudaEventRecord(r->ready, r->user_stream));
     for (auto& l : r->lane) GSR_CUDA_TRY(cudaStreamWaitEvent(l.stream, r->ready, 0));
     long long total = 0;
-    for (int v = 0; v < n_views; ++v) {
+    int rc_err = 0;
+    for (int v = 0; v < n_views && rc_err == 0; ++v) {
         Lane& l = r->lane[v % LANES];
-        int rc = render_one(r, l, cameras + (size_t)v * CAM_FLOATS, tan_fovx, tan_fovy, l.frame_dev, nullptr);
-        if (rc < 0) return rc;
-        GSR_CUDA_TRY(cudaMemcpyAsync(out_color_host + (size_t)v * frame, l.frame_dev, frame * sizeof(float),
-                                     cudaMemcpyDeviceToHost, l.stream));
+        const int b = l.frame_ix;
+        l.frame_ix ^= 1;
+        // the frame buffer is free again once the copy issued from it two views ago has drained
+        if (l.copy_pending[b]) GSR_CUDA_TRY(cudaStreamWaitEvent(l.stream, l.copied[b], 0));
+        int rc = render_one(r, l, cameras + (size_t)v * CAM_FLOATS, tan_fovx, tan_fovy, l.frame_dev[b], nullptr);
+        if (rc < 0) { rc_err = rc; break; }
+        GSR_CUDA_TRY(cudaEventRecord(l.rendered[b], l.stream));
+        GSR_CUDA_TRY(cudaStreamWaitEvent(l.copy_stream, l.rendered[b], 0));
+        GSR_CUDA_TRY(cudaMemcpyAsync(out_color_host + (size_t)v * frame, l.frame_dev[b], frame * sizeof(float),
+                                     cudaMemcpyDeviceToHost, l.copy_stream));
+        GSR_CUDA_TRY(cudaEventRecord(l.copied[b], l.copy_stream));
+        l.copy_pending[b] = true;
         if (num_rendered) num_rendered[v] = rc;
         total += rc;
     }
-    for (auto& l : r->lane) GSR_CUDA_TRY(cudaStreamSynchronize(l.stream));
+    for (auto& l : r->lane) {
+        GSR_CUDA_TRY(cudaStreamSynchronize(l.copy_stream));
+        GSR_CUDA_TRY(cudaStreamSynchronize(l.stream));
+        l.copy_pending[0] = l.copy_pending[1] = false;
+    }
+    if (rc_err) return rc_err;
     return (int)(total > 0x7fffffffLL ? 0x7fffffff : total);
 }
 

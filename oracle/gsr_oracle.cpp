@@ -300,27 +300,44 @@ void computeColorFromSH(int idx, int deg, int max_coeffs, const V3& pos, const f
     float res[3];
     float x = dir.x, y = dir.y, z = dir.z;
     float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    // Basis factors exactly as upstream forward.cu computeColorFromSH writes them (sign folded in).
+    float bf[16] = {SH_C0,
+                    -(SH_C1 * y),
+                    SH_C1 * z,
+                    -(SH_C1 * x),
+                    SH_C2[0] * xy,
+                    SH_C2[1] * yz,
+                    SH_C2[2] * ((2.0f * zz - xx) - yy),
+                    SH_C2[3] * xz,
+                    SH_C2[4] * (xx - yy),
+                    (SH_C3[0] * y) * (3.0f * xx - yy),
+                    (SH_C3[1] * xy) * z,
+                    (SH_C3[2] * y) * ((4.0f * zz - xx) - yy),
+                    (SH_C3[3] * z) * ((2.0f * zz - 3.0f * xx) - 3.0f * yy),
+                    (SH_C3[4] * x) * ((4.0f * zz - xx) - yy),
+                    (SH_C3[5] * z) * (xx - yy),
+                    (SH_C3[6] * x) * (xx - 3.0f * yy)};
+    // Summation order.  Upstream writes one left-to-right chain per channel, which nvcc (default -fmad=true)
+    // contracts into FMAs in an order of its own choosing, so no association is canonical for the contract;
+    // the colours only feed the image (tolerance 1/255).  This restatement fixes the order the sm_100a kernel
+    // uses: four groups of four coefficients, each an FMA chain, added pairwise:
+    //   s_q = fma(b[4q+3],c[4q+3], fma(b[4q+2],c[4q+2], fma(b[4q+1],c[4q+1], b[4q]*c[4q])))
+    //   rgb = ((s0 + s1) + (s2 + s3)) + 0.5            (coefficients beyond the active degree count as 0)
+    // tests/test_oracle_kat.py (KAT-5) holds it to the FP64 real SH basis.
+    const int ncoef = std::min(max_coeffs, (deg + 1) * (deg + 1));
+    for (int k = 0; k < 16; ++k)
+        if (k >= ncoef) bf[k] = 0.0f;
     for (int c = 0; c < 3; ++c) {
-        auto S = [&](int k) { return sh[k * 3 + c]; };
-        float result = SH_C0 * S(0);
-        if (deg > 0) {
-            result = ((result - (SH_C1 * y) * S(1)) + (SH_C1 * z) * S(2)) - (SH_C1 * x) * S(3);
-            if (deg > 1) {
-                result = ((((result + (SH_C2[0] * xy) * S(4)) + (SH_C2[1] * yz) * S(5)) +
-                           (SH_C2[2] * ((2.0f * zz - xx) - yy)) * S(6)) +
-                          (SH_C2[3] * xz) * S(7)) +
-                         (SH_C2[4] * (xx - yy)) * S(8);
-                if (deg > 2) {
-                    result = ((((((result + ((SH_C3[0] * y) * (3.0f * xx - yy)) * S(9)) +
-                                  ((SH_C3[1] * xy) * z) * S(10)) +
-                                 ((SH_C3[2] * y) * ((4.0f * zz - xx) - yy)) * S(11)) +
-                                ((SH_C3[3] * z) * ((2.0f * zz - 3.0f * xx) - 3.0f * yy)) * S(12)) +
-                               ((SH_C3[4] * x) * ((4.0f * zz - xx) - yy)) * S(13)) +
-                              ((SH_C3[5] * z) * (xx - yy)) * S(14)) +
-                             ((SH_C3[6] * x) * (xx - 3.0f * yy)) * S(15);
-                }
-            }
+        auto S = [&](int k) { return k < ncoef ? sh[k * 3 + c] : 0.0f; };
+        float part[4];
+        for (int q = 0; q < 4; ++q) {
+            float acc = bf[4 * q] * S(4 * q);
+            acc = std::fmaf(bf[4 * q + 1], S(4 * q + 1), acc);
+            acc = std::fmaf(bf[4 * q + 2], S(4 * q + 2), acc);
+            acc = std::fmaf(bf[4 * q + 3], S(4 * q + 3), acc);
+            part[q] = acc;
         }
+        float result = (part[0] + part[1]) + (part[2] + part[3]);
         result += 0.5f;
         res[c] = result;
     }

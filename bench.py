@@ -334,7 +334,7 @@ def main():
     tanx, tany = cams[0].tan_fovx, cams[0].tan_fovy
     packed = np.stack([c.packed() for c in cams]).astype(np.float32)
     frame_bytes = 3 * W * H * 4
-    nbuf = min(K, 8)  # device output ring for the resident-input measurement
+    nbuf = min(K, 40)  # device output ring for the resident-input measurement (same views per call as the e2e leg)
     out_dev = torch.empty((nbuf, 3, H, W), dtype=torch.float32, device=dev)
 
     def barrier():
@@ -412,7 +412,7 @@ def main():
             if i >= 2:
                 stage_runs.append(tm)
         keys = ("preprocess_ms", "scan_ms", "duplicate_ms", "sort_ms", "ranges_ms", "blend_ms", "total_ms",
-                "sort_hist_ms", "depth_sort_ms", "expand_ms")
+                "sort_hist_ms", "depth_sort_ms", "expand_ms", "expand_count_ms", "expand_fill_ms")
         st = {k: statistics.mean(r[k] for r in stage_runs) for k in keys}
         passes = stage_runs[0]["sort_passes"]
         dpasses = stage_runs[0]["depth_passes"]
@@ -469,7 +469,9 @@ def main():
             "frame_serial_ms": st["total_ms"],
         }
         if Rc:
-            stages["expand"] = {"ms": st["expand_ms"], "GB/s": gbs(ab["expand"], st["expand_ms"])}
+            stages["expand"] = {"ms": st["expand_ms"], "GB/s": gbs(ab["expand"], st["expand_ms"]),
+                                "count_ms": st["expand_count_ms"], "fill_ms": st["expand_fill_ms"],
+                                "fill_GB/s": gbs(ab["expand_fill"], st["expand_fill_ms"])}
         for v in stages.values():
             if isinstance(v, dict) and v.get("GB/s"):
                 v["frac_of_peak"] = v["GB/s"] / peak
@@ -487,10 +489,11 @@ def main():
                 "duplicate_sorted_kernel": (ab["duplicate"], st["duplicate_ms"])}
         share = {"preprocess_kernel": st["preprocess_ms"], "duplicate_sorted_kernel": st["duplicate_ms"]}
         if Rc:
-            # the count / scan kernels of the expansion are a small share; the fill pass is rated on the expansion's
-            # whole time (an upper bound of its own), so its fraction is a lower bound
-            cand["expand_fill_kernel"] = (ab["expand_fill"], st["expand_ms"])
-            share["expand_fill_kernel"] = st["expand_ms"]
+            # the two streaming kernels of the expansion, each on its own launch duration
+            cand["expand_fill_kernel"] = (ab["expand_fill"], st["expand_fill_ms"])
+            share["expand_fill_kernel"] = st["expand_fill_ms"]
+            cand["expand_count_kernel"] = (ab["expand_count"], st["expand_count_ms"])
+            share["expand_count_kernel"] = st["expand_count_ms"]
         else:
             osw = "onesweep_kernel<u32> (mean of %d tile-digit passes over R pairs)" % tpasses
             cand[osw] = ((ab["tile_pass"] * (tpasses - 1) + ab["tile_pass_last"]) / max(tpasses, 1), statistics.mean(tile_ms))
@@ -506,6 +509,16 @@ def main():
                 roof["traffic"] = json.load(open(ncu_traffic)).get(dom.split(" ")[0])
             except Exception:
                 pass
+
+        # blend: FP32/MUFU issue bound, no HBM or tensor roofline applies; rate = staged (tile, splat) pairs per second,
+        # pipe utilisation from the committed ncu capture of the same workload (profiles/pipes.json)
+        stages["blend"]["pairs_per_s"] = R / (st["blend_ms"] / 1e3) if st["blend_ms"] > 0 else None
+        try:
+            pipes = json.load(open(os.path.join(ROOT, "profiles", "pipes.json")))
+            if args.workload in ("C2", "C4") and not args.simple_blend:
+                stages["blend"]["ncu"] = pipes.get("blend_culled_kernel")
+        except Exception:
+            pass
 
         cpu = None
         if not args.no_cpu_baseline and world == 1:

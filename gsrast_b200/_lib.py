@@ -29,7 +29,8 @@ class StageTimes(C.Structure):
                [("num_rendered", C.c_int), ("sort_passes", C.c_int), ("kernel_launches", C.c_int),
                 ("sort_hist_ms", C.c_float), ("sort_pass_ms", C.c_float * 8),
                 ("depth_sort_ms", C.c_float), ("depth_passes", C.c_int),
-                ("expand_ms", C.c_float), ("num_coarse", C.c_int), ("binning_mode", C.c_int)]
+                ("expand_ms", C.c_float), ("num_coarse", C.c_int), ("binning_mode", C.c_int),
+                ("expand_count_ms", C.c_float), ("expand_fill_ms", C.c_float)]
 
     def as_dict(self):
         d = {n: getattr(self, n) for n, _ in self._fields_}

@@ -35,6 +35,9 @@ namespace gsr {
 
 namespace {
 
+#ifndef GSR_FILL_FAST
+#define GSR_FILL_FAST 0
+#endif
 constexpr int EXP_THREADS = 256;
 constexpr int EXP_WARPS = EXP_THREADS / 32;
 constexpr int EXP_CHUNK = 256;                 // records per chunk: one per thread, one warp-step (32 records) per warp
@@ -460,6 +463,59 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_fill_kernel(const ExpandAr
         if (tid < BIN_TILES) { s_gbase[tid] = gb; s_tileid[tid] = tile; }
     }
     __syncthreads();
+#if GSR_FILL_FAST
+    // Fast path (chunks of at most EXP_CAP pairs, i.e. nearly all of them): a single round, no further table
+    // building.  Thread (tile t = tid & 63, quarter q) has t = 32 * (warp & 1) + lane, so every warp derives what
+    // its threads need from the ballots on its own — its half's per-tile counts (scanned across the lanes) and the
+    // other half's total — instead of steps 2-3 and the round prologue below with their three barriers.
+    {
+        const int half = warp & 1, q2 = (warp >> 1) * EXP_WS_PER_Q;
+        uint32_t mine_before = 0, mine_tot = 0, other_tot = 0;
+#pragma unroll
+        for (int ws = 0; ws < EXP_WS; ++ws) {
+            const uint32_t n_own = (uint32_t)__popc(s_bal[ws][half * 32 + lane]);
+            const uint32_t n_oth = (uint32_t)__popc(s_bal[ws][(half ^ 1) * 32 + lane]);
+            if (ws < q2) mine_before += n_own;
+            mine_tot += n_own;
+            other_tot += n_oth;
+        }
+        uint32_t inc = mine_tot;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, inc, dd);
+            if (lane >= dd) inc += up;
+        }
+        const uint32_t own_T = __shfl_sync(0xffffffffu, inc, 31);
+        const uint32_t other_T = __reduce_add_sync(0xffffffffu, other_tot);
+        const uint32_t total = own_T + other_T;  // identical in every warp
+        if (total <= (uint32_t)EXP_CAP) {
+            const int t = half * 32 + lane;
+            const uint32_t o = inc - mine_tot + (half ? other_T : 0u);  // staged offset of tile t's run
+            if (q2 == 0) s_gadj[t] = s_gbase[t] - o;                    // final position = s_gadj[t] + staged index
+            uint32_t slot = o + mine_before;
+            const int w1 = min(nws, q2 + EXP_WS_PER_Q);
+            for (int ws = q2; ws < w1; ++ws) {
+                uint32_t bits = s_bal[ws][t];
+                while (bits) {
+                    const int l = __ffs((int)bits) - 1;
+                    bits &= bits - 1u;
+                    s_out[slot] = s_rec[ws * 32 + l];
+                    s_t[slot] = (unsigned char)t;
+                    ++slot;
+                }
+            }
+            __syncthreads();
+            for (uint32_t j = tid; j < total; j += EXP_THREADS) {
+                const int tt = s_t[j];
+                const uint32_t g = s_gadj[tt] + j;
+                const uint2 o2 = s_out[j];
+                a.keys_out[g] = ((uint64_t)s_tileid[tt] << 32) | (uint64_t)o2.y;  // GSCuda.cu:466-471
+                a.vals_out[g] = o2.x;
+            }
+            return;
+        }
+    }
+#endif
     // 2. per tile: prefix over the warp-steps; pairs per warp-step
     if (tid < BIN_TILES) {
         uint32_t run = 0;
@@ -552,7 +608,7 @@ size_t expand_temp_bytes(size_t R) {
            align128(max_chunks(R) * EXP_WS * BIN_TILES * sizeof(uint32_t)) + align128(R * sizeof(uint2));
 }
 
-int launch_bin_expand(const ExpandPlan& p, cudaStream_t s) {
+int launch_bin_expand(const ExpandPlan& p, cudaStream_t s, cudaEvent_t* ev) {
     const int nbins = p.bins_x * p.bins_y;
     if (nbins < 1 || nbins > MAX_BINS || p.n_records == 0 || p.n_records > p.num_rendered) return GSR_ERR_INVALID_ARG;
     if (p.n_records >= ((size_t)1 << 31)) return GSR_ERR_TOO_MANY_PAIRS;
@@ -581,13 +637,17 @@ int launch_bin_expand(const ExpandPlan& p, cudaStream_t s) {
     a.keys_out = p.keys_out;
     a.vals_out = p.vals_out;
     a.grid_x = p.grid_x; a.grid_y = p.grid_y; a.bins_x = p.bins_x;
+    if (ev) cudaEventRecord(ev[0], s);
     GSR_CUDA_TRY(launch_pdl(expand_count_kernel, dim3(nchunk_bound), dim3(EXP_THREADS), 0, s, a));
+    if (ev) cudaEventRecord(ev[1], s);
     ++launches;
     GSR_CUDA_TRY(launch_pdl(expand_scan_kernel, dim3(nbins), dim3(EXP_THREADS), 0, s, (const uint32_t*)t.bin_chunk_first,
                             t.chunk_counts, p.tile_counts, p.grid_x, p.grid_y, p.bins_x, nbins,
                             reinterpret_cast<uint2*>(p.ranges), p.r1_quirk ? 1 : 0, t.done_counter));
     ++launches;
+    if (ev) cudaEventRecord(ev[2], s);
     GSR_CUDA_TRY(launch_pdl(expand_fill_kernel, dim3(nchunk_bound), dim3(EXP_THREADS), 0, s, a));
+    if (ev) cudaEventRecord(ev[3], s);
     ++launches;
     return launches;
 }

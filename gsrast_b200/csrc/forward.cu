@@ -236,7 +236,7 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
     const int bin_bits = (int)gsr_get_higher_msb((uint32_t)nbins);
     const int tile_passes = sort_num_passes(bin_mode ? bin_bits : tile_bits);
     const int depth_passes = sort_num_passes(32);
-    cudaEvent_t sort_ev[12];
+    cudaEvent_t sort_ev[16];  // [0..11] the two sort halves, [12..15] count / fill kernels of the bin expansion
     const bool sort_timed = tm.on;
     if (sort_timed)
         for (auto& e : sort_ev) cudaEventCreate(&e);
@@ -389,7 +389,7 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         ep.tile_counts = img.tile_order; ep.ranges = img.ranges;
         ep.keys_out = bin.point_list_keys; ep.vals_out = bin.point_list;
         ep.r1_quirk = compat && R == 1;
-        GSR_STAGE(launch_bin_expand(ep, s));
+        GSR_STAGE(launch_bin_expand(ep, s, sort_timed ? sort_ev + 12 : nullptr));
         tm.mark();  // 6
     } else {
         uint32_t* tile_hist = sort32_prepare(tile_temp, (size_t)R, tile_bits, s);
@@ -440,6 +440,10 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         t->sort_ms = tm.ms(4, 5);
         t->ranges_ms = bin_mode ? 0.f : tm.ms(5, 6);
         t->expand_ms = bin_mode ? tm.ms(5, 6) : 0.f;
+        if (bin_mode && Rc) {
+            cudaEventElapsedTime(&t->expand_count_ms, sort_ev[12], sort_ev[13]);
+            cudaEventElapsedTime(&t->expand_fill_ms, sort_ev[14], sort_ev[15]);
+        }
         t->num_coarse = (int)Rc;
         t->binning_mode = bin_mode ? 0 : 1;
         t->blend_ms = tm.ms(6, 7);

@@ -162,7 +162,8 @@ struct ExpandPlan {
     uint32_t* vals_out;           // [R]
     bool r1_quirk;                // GSRast-compat: a frame of exactly one pair never closes its range (GSCuda.cu:533-536)
 };
-int launch_bin_expand(const ExpandPlan& plan, cudaStream_t s);
+// ev (optional, 4 events): recorded before / after the count kernel and before / after the fill kernel
+int launch_bin_expand(const ExpandPlan& plan, cudaStream_t s, cudaEvent_t* ev = nullptr);
 
 struct BlendParams {
     int W, H, grid_x, grid_y;

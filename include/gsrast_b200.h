@@ -97,6 +97,8 @@ typedef struct gsr_stage_times {
     float expand_ms;
     int num_coarse;
     int binning_mode;       /* 0 = bin expansion, 1 = radix passes over the pairs */
+    float expand_count_ms;  /* expand_count_kernel alone (one launch) */
+    float expand_fill_ms;   /* expand_fill_kernel alone (one launch): the pass that writes the 12 B/pair result */
 } gsr_stage_times;
 
 /* Same call with explicit strides / flags (superset of the two above). */

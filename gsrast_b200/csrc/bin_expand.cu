@@ -36,7 +36,7 @@ namespace gsr {
 namespace {
 
 #ifndef GSR_FILL_FAST
-#define GSR_FILL_FAST 0
+#define GSR_FILL_FAST 1
 #endif
 constexpr int EXP_THREADS = 256;
 constexpr int EXP_WARPS = EXP_THREADS / 32;
@@ -275,8 +275,11 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_count_kernel(const ExpandA
     gsr_pdl_wait();
     gsr_pdl_launch_dependents();
     const uint32_t c = blockIdx.x;
-    if (c >= __ldg(a.num_chunks)) return;
+    // descriptor fetched alongside the chunk count (the table holds max_chunks(R) >= gridDim.x entries): one
+    // dependent round trip less in a kernel that is a chain of them
+    const uint32_t nchunks = __ldg(a.num_chunks);
     const uint4 d = __ldg(a.chunk_desc + c);
+    if (c >= nchunks) return;
     if (tid < BIN_TILES) s_cnt[tid] = 0;
     __syncthreads();
     const int bx8 = (int)(d.x % (uint32_t)a.bins_x) << BIN_SHIFT, by8 = (int)(d.x / (uint32_t)a.bins_x) << BIN_SHIFT;
@@ -439,8 +442,9 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_fill_kernel(const ExpandAr
     gsr_pdl_wait();
     gsr_pdl_launch_dependents();
     const uint32_t c = blockIdx.x;
-    if (c >= __ldg(a.num_chunks)) return;
-    const uint4 d = __ldg(a.chunk_desc + c);
+    const uint32_t nchunks = __ldg(a.num_chunks);
+    const uint4 d = __ldg(a.chunk_desc + c);  // in bounds for every CTA of the grid (see expand_count_kernel)
+    if (c >= nchunks) return;
     const int bx8 = (int)(d.x % (uint32_t)a.bins_x) << BIN_SHIFT, by8 = (int)(d.x / (uint32_t)a.bins_x) << BIN_SHIFT;
     const int nws = (int)((d.z - d.y + 31u) >> 5);
 

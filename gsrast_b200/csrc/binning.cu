@@ -209,7 +209,9 @@ __global__ void __launch_bounds__(PRE_THREADS) duplicate_sorted_kernel(
     const uint32_t* __restrict__ block_offsets, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
     uint32_t* __restrict__ hist, const int tile_bits, const uint32_t* __restrict__ n_sorted) {
     __shared__ uint32_t s_excl[DUP_GAUSS + 1];
-    __shared__ uint32_t s_warp[PRE_THREADS / 32];
+    // 16-byte aligned: the compiler reads the 8 warp sums with LDS.128, which otherwise straddles s_excl[DUP_GAUSS]
+    // (unused lane of the vector, but compute-sanitizer racecheck rightly flags the overlap with its later store)
+    __shared__ __align__(16) uint32_t s_warp[PRE_THREADS / 32];
     __shared__ uint32_t s_gid[DUP_GAUSS];
     __shared__ uint32_t s_origin[DUP_GAUSS];  // miny << 16 | minx
     __shared__ uint32_t s_width[DUP_GAUSS];

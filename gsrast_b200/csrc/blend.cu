@@ -125,9 +125,10 @@ __device__ __forceinline__ float max_power_in_box(float a, float b, float c, flo
 
 // Cull-bound arithmetic.  The bounds carry multiplicative and additive slack (1.0001 / 0.01 px / 1e-3 in the
 // exponent), orders of magnitude above the 2-ulp error of the approximate units, and the 1-D optimum enters
-// `power` only to second order — so MUFU.RSQ/RCP-based sqrt and division replace the IEEE sequences.
+// `power` only to second order — so MUFU-based sqrt and division replace the IEEE sequences
+// (profiles/r01f_ab.txt: blend 0.356 -> 0.351 ms at C2).
 #ifndef GSR_BLEND_FASTCULL
-#define GSR_BLEND_FASTCULL 0
+#define GSR_BLEND_FASTCULL 1
 #endif
 __device__ __forceinline__ float cull_sqrt(float x) {
 #if GSR_BLEND_FASTCULL
@@ -169,21 +170,9 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
 #ifndef GSR_BLEND_MINB
 #define GSR_BLEND_MINB 5
 #endif
-// GSR_BLEND_DB=1: two staging buffers, ONE barrier per batch.  Batch r is staged into buffer r&1 while slower warps
-// may still be blending batch r-1 out of the other one; the barrier behind the staging also carries the
-// "every warp has saturated" vote.  A shared counter of finished warps lets the last warp (the only one whose
-// staging would delay the exit) skip the staging of a batch nobody will read.
-#ifndef GSR_BLEND_DB
-#define GSR_BLEND_DB 0
-#endif
-constexpr int BLEND_NBUF = GSR_BLEND_DB ? 2 : 1;
 __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_kernel(const BlendParams p) {
-    __shared__ float4 s_splat_all[BLEND_NBUF][BATCH * 3];
-    __shared__ unsigned char s_mask_all[BLEND_NBUF][BATCH];     // bit w: splat can reach warp w's 8x4 sub-rectangle
-#if GSR_BLEND_DB
-    __shared__ int s_done_warps;
-    if (threadIdx.x == 0) s_done_warps = 0;
-#endif
+    __shared__ float4 s_splat[BATCH * 3];
+    __shared__ unsigned char s_mask[BATCH];                     // bit w: splat can reach warp w's 8x4 sub-rectangle
     __shared__ unsigned short s_list[BLEND_THREADS / 32][BATCH]; // per warp: byte offsets (48 * staged index) of its candidates
 
     const int tile = p.tile_order ? (int)__ldg(p.tile_order + blockIdx.x) : (int)blockIdx.x;
@@ -199,7 +188,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
     unsigned short* my_list = s_list[warp];
     // 32-bit shared-window address of the staging buffer, formed once: the inner loop then issues plain
     // LDS [reg + imm] (a generic float4* made the compiler re-derive the window base inside the loop)
-    uint32_t splat_base = (uint32_t)__cvta_generic_to_shared(s_splat_all[0]);
+    uint32_t splat_base = (uint32_t)__cvta_generic_to_shared(s_splat);
     uint32_t list_base = (uint32_t)__cvta_generic_to_shared(my_list);
     float t_min = p.t_min;
     // opaque to the optimiser, so the three values live in registers instead of being re-materialised
@@ -230,29 +219,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
         n_c0 = __ldg(col); n_c1 = __ldg(col + 1); n_c2 = __ldg(col + 2);
     }
 
-#if GSR_BLEND_DB
-    __syncthreads();  // s_done_warps = 0 visible
-    if (warp_done && lane == 0) atomicAdd(&s_done_warps, 1);  // warps entirely outside the image
-    bool counted = warp_done;
-    const uint32_t splat_base0 = splat_base;
-#endif
     for (int r = 0; r < rounds; ++r) {
-#if GSR_BLEND_DB
-        float4* s_splat = s_splat_all[r & 1];
-        unsigned char* s_mask = s_mask_all[r & 1];
-        splat_base = splat_base0 + (uint32_t)((r & 1) * (BATCH * 48));
-        if (warp_done && !counted) {
-            counted = true;
-            if (lane == 0) atomicAdd(&s_done_warps, 1);
-        }
-        // monotone counter: 8 means the vote below is unanimous, so this batch is never read
-        const bool skip_stage = *reinterpret_cast<volatile int*>(&s_done_warps) == BLEND_THREADS / 32;
-#else
-        float4* s_splat = s_splat_all[0];
-        unsigned char* s_mask = s_mask_all[0];
-        constexpr bool skip_stage = false;
         if (__syncthreads_and(warp_done)) break;
-#endif
         const int progress = r * BATCH + tid;
         uint32_t m = 0;
         const float2 xy = n_xy;
@@ -265,7 +233,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
             const float* col = p.colors + (size_t)id * 3;
             n_c0 = __ldg(col); n_c1 = __ldg(col + 1); n_c2 = __ldg(col + 2);
         }
-        if (progress < total && !skip_stage) {
+        if (progress < total) {
             const float a = co.x, b = co.y, c = co.z, o = co.w;
             s_splat[3 * tid + 0] = make_float4(xy.x, xy.y, -0.5f * LOG2E * a, -LOG2E * b);
             s_splat[3 * tid + 1] = make_float4(-0.5f * LOG2E * c, o, cr, cg);
@@ -308,11 +276,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
             }
         }
         s_mask[tid] = (unsigned char)m;
-#if GSR_BLEND_DB
-        if (__syncthreads_and(warp_done)) break;
-#else
         __syncthreads();
-#endif
 
         if (!warp_done) {
             // this warp's candidates of the batch, in order

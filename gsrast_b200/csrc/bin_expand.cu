@@ -60,7 +60,7 @@ struct ExpandTemp {
     uint2* rec_data;            // [R] per record: Gaussian id, depth bits (gathered once, by the count pass)
 };
 
-size_t max_chunks(size_t R) { return R / EXP_CHUNK + std::min<size_t>((size_t)MAX_BINS, R) + 1; }
+size_t max_chunks(size_t R) { return R / EXP_CHUNK + std::min<size_t>((size_t)MAX_BINS, R) + 2; }  // + 1 spare: kernels read the descriptor before the bound check
 
 ExpandTemp carve(char* temp, size_t R) {
     ExpandTemp t;
@@ -269,38 +269,64 @@ struct ExpandArgs {
 // Thread i of chunk c owns record i: gathers its tile rect and depth bits (the only random accesses of the
 // expansion), builds the tile mask of the bin; every warp transposes its 32 masks into 64 ballots.  Left for
 // the fill pass: the ballots, (id, depth) per record, and the chunk's pairs per tile.
+#ifndef GSR_COUNT_CHUNKS
+#define GSR_COUNT_CHUNKS 2   // chunks per CTA: their dependent load chains (descriptor -> id -> rect, depth) overlap
+#endif
+constexpr int CNT_CHUNKS = GSR_COUNT_CHUNKS;
 __global__ void __launch_bounds__(EXP_THREADS) expand_count_kernel(const ExpandArgs a) {
-    __shared__ uint32_t s_cnt[BIN_TILES];
+    __shared__ uint32_t s_cnt[CNT_CHUNKS][BIN_TILES];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     gsr_pdl_wait();
     gsr_pdl_launch_dependents();
-    const uint32_t c = blockIdx.x;
-    // descriptor fetched alongside the chunk count (the table holds max_chunks(R) >= gridDim.x entries): one
-    // dependent round trip less in a kernel that is a chain of them
+    // descriptors fetched alongside the chunk count (the table holds max_chunks(R) entries and the grid is
+    // rounded up inside that bound): one dependent round trip less in a kernel that is a chain of them
     const uint32_t nchunks = __ldg(a.num_chunks);
-    const uint4 d = __ldg(a.chunk_desc + c);
-    if (c >= nchunks) return;
-    if (tid < BIN_TILES) s_cnt[tid] = 0;
+    const uint32_t cbase = blockIdx.x * CNT_CHUNKS;
+    uint4 d[CNT_CHUNKS];
+#pragma unroll
+    for (int k = 0; k < CNT_CHUNKS; ++k) d[k] = __ldg(a.chunk_desc + cbase + k);
+    if (cbase >= nchunks) return;
+    if (tid < CNT_CHUNKS * BIN_TILES) (&s_cnt[0][0])[tid] = 0;
     __syncthreads();
-    const int bx8 = (int)(d.x % (uint32_t)a.bins_x) << BIN_SHIFT, by8 = (int)(d.x / (uint32_t)a.bins_x) << BIN_SHIFT;
-    const uint32_t r = d.y + (uint32_t)tid;
-    uint64_t m = 0ull;
-    if (r < d.z) {
-        const uint32_t id = __ldg(a.rec_ids + r);
-        const uint2 rect = __ldg(a.tile_rects + id);
-        const uint32_t dep = __ldg(a.depths + id);
-        m = bin_mask(rect, bx8, by8);
-        a.rec_data[r] = make_uint2(id, dep);
+    // every chunk's id load, then every chunk's gathers: the chains of the CTA's chunks run side by side
+    uint32_t id[CNT_CHUNKS];
+    bool have[CNT_CHUNKS];
+#pragma unroll
+    for (int k = 0; k < CNT_CHUNKS; ++k) {
+        const uint32_t r = d[k].y + (uint32_t)tid;
+        have[k] = (cbase + k < nchunks) && r < d[k].z;
+        id[k] = have[k] ? __ldg(a.rec_ids + r) : 0u;
     }
-    const uint32_t bl = warp_transpose32((uint32_t)m, lane);
-    const uint32_t bh = warp_transpose32((uint32_t)(m >> 32), lane);
-    uint32_t* bal = a.chunk_ballots + ((size_t)c * EXP_WS + warp) * BIN_TILES;
-    bal[lane] = bl;
-    bal[32 + lane] = bh;
-    if (bl) atomicAdd(&s_cnt[lane], (uint32_t)__popc(bl));
-    if (bh) atomicAdd(&s_cnt[32 + lane], (uint32_t)__popc(bh));
+    uint2 rect[CNT_CHUNKS];
+    uint32_t dep[CNT_CHUNKS];
+#pragma unroll
+    for (int k = 0; k < CNT_CHUNKS; ++k) {
+        rect[k] = have[k] ? __ldg(a.tile_rects + id[k]) : make_uint2(0u, 0u);
+        dep[k] = have[k] ? __ldg(a.depths + id[k]) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < CNT_CHUNKS; ++k) {
+        const uint32_t c = cbase + k;
+        if (c >= nchunks) break;  // block-uniform
+        const int bx8 = (int)(d[k].x % (uint32_t)a.bins_x) << BIN_SHIFT, by8 = (int)(d[k].x / (uint32_t)a.bins_x) << BIN_SHIFT;
+        uint64_t m = 0ull;
+        if (have[k]) {
+            m = bin_mask(rect[k], bx8, by8);
+            a.rec_data[d[k].y + (uint32_t)tid] = make_uint2(id[k], dep[k]);
+        }
+        const uint32_t bl = warp_transpose32((uint32_t)m, lane);
+        const uint32_t bh = warp_transpose32((uint32_t)(m >> 32), lane);
+        uint32_t* bal = a.chunk_ballots + ((size_t)c * EXP_WS + warp) * BIN_TILES;
+        bal[lane] = bl;
+        bal[32 + lane] = bh;
+        if (bl) atomicAdd(&s_cnt[k][lane], (uint32_t)__popc(bl));
+        if (bh) atomicAdd(&s_cnt[k][32 + lane], (uint32_t)__popc(bh));
+    }
     __syncthreads();
-    if (tid < BIN_TILES) a.chunk_counts[(size_t)c * BIN_TILES + tid] = s_cnt[tid];
+    if (tid < CNT_CHUNKS * BIN_TILES) {
+        const uint32_t c = cbase + (uint32_t)(tid / BIN_TILES);
+        if (c < nchunks) a.chunk_counts[(size_t)c * BIN_TILES + (tid % BIN_TILES)] = (&s_cnt[0][0])[tid];
+    }
 }
 
 // ---- scans: over the chunks of every bin per tile, then over the tiles -> ranges ---------------------------
@@ -642,7 +668,8 @@ int launch_bin_expand(const ExpandPlan& p, cudaStream_t s, cudaEvent_t* ev) {
     a.vals_out = p.vals_out;
     a.grid_x = p.grid_x; a.grid_y = p.grid_y; a.bins_x = p.bins_x;
     if (ev) cudaEventRecord(ev[0], s);
-    GSR_CUDA_TRY(launch_pdl(expand_count_kernel, dim3(nchunk_bound), dim3(EXP_THREADS), 0, s, a));
+    GSR_CUDA_TRY(launch_pdl(expand_count_kernel, dim3((nchunk_bound + CNT_CHUNKS - 1) / CNT_CHUNKS), dim3(EXP_THREADS), 0, s,
+                            a));
     if (ev) cudaEventRecord(ev[1], s);
     ++launches;
     GSR_CUDA_TRY(launch_pdl(expand_scan_kernel, dim3(nbins), dim3(EXP_THREADS), 0, s, (const uint32_t*)t.bin_chunk_first,

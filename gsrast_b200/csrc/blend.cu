@@ -170,6 +170,11 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
 #ifndef GSR_BLEND_MINB
 #define GSR_BLEND_MINB 5
 #endif
+#ifdef GSR_BLEND_STATS
+// diagnostics build only (tools/blend_stats.py): [0] tile-rounds staged, [1] warp-rounds that walked a list,
+// [2] candidates listed (warp level), [3] tile-rounds the deepest n_contrib of the tile needed
+__device__ unsigned long long g_blend_stats[4];
+#endif
 __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_kernel(const BlendParams p) {
     __shared__ float4 s_splat[BATCH * 3];
     __shared__ unsigned char s_mask[BATCH];                     // bit w: splat can reach warp w's 8x4 sub-rectangle
@@ -221,6 +226,9 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
 
     for (int r = 0; r < rounds; ++r) {
         if (__syncthreads_and(warp_done)) break;
+#ifdef GSR_BLEND_STATS
+        if (tid == 0) atomicAdd(&g_blend_stats[0], 1ull);
+#endif
         const int progress = r * BATCH + tid;
         uint32_t m = 0;
         const float2 xy = n_xy;
@@ -289,6 +297,9 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
                 n += __popc(bits);
             }
             __syncwarp();
+#ifdef GSR_BLEND_STATS
+            if (lane == 0) { atomicAdd(&g_blend_stats[1], 1ull); atomicAdd(&g_blend_stats[2], (unsigned long long)n); }
+#endif
             // Branch-free inner loop.  A terminated pixel carries its final transmittance as a NEGATIVE T:
             // then w = alpha*T and T - w are negative, "T - w >= t_min" fails, nothing is blended, and
             // no separate `done` flag has to be tested.  Per candidate: LDS.U16, 2 LDS.128, 8 FP32 for the
@@ -328,6 +339,17 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
             if (last_off != 0xffffffffu) last = (uint32_t)(r * BATCH + 1) + last_off / 48u;
         }
     }
+#ifdef GSR_BLEND_STATS
+    {
+        __shared__ unsigned s_maxlast;
+        __syncthreads();
+        if (tid == 0) s_maxlast = 0;
+        __syncthreads();
+        atomicMax(&s_maxlast, last);
+        __syncthreads();
+        if (tid == 0) atomicAdd(&g_blend_stats[3], (unsigned long long)((s_maxlast + BATCH - 1) / BATCH));
+    }
+#endif
     T = fabsf(T);
     if (inside) {
         const size_t pix = (size_t)pix_y * p.W + pix_x;
@@ -352,6 +374,18 @@ __global__ void fill_background_kernel(int n, const float* __restrict__ backgrou
 }
 
 }  // namespace
+
+#ifdef GSR_BLEND_STATS
+extern "C" int gsr_debug_blend_stats(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_blend_stats, sizeof(g_blend_stats));
+    if (reset) {
+        unsigned long long z[4] = {0, 0, 0, 0};
+        cudaMemcpyToSymbol(g_blend_stats, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
 
 int launch_blend(const BlendParams& p, bool simple, cudaStream_t s) {
     const int tiles = p.grid_x * p.grid_y;

@@ -667,6 +667,9 @@ int launch_bin_expand(const ExpandPlan& p, cudaStream_t s, cudaEvent_t* ev) {
     a.keys_out = p.keys_out;
     a.vals_out = p.vals_out;
     a.grid_x = p.grid_x; a.grid_y = p.grid_y; a.bins_x = p.bins_x;
+    GSR_CARVEOUT(expand_count_kernel, "COUNT", -1);
+    GSR_CARVEOUT(expand_fill_kernel, "FILL", -1);
+    GSR_CARVEOUT(expand_scan_kernel, "ESCAN", -1);
     if (ev) cudaEventRecord(ev[0], s);
     GSR_CUDA_TRY(launch_pdl(expand_count_kernel, dim3((nchunk_bound + CNT_CHUNKS - 1) / CNT_CHUNKS), dim3(EXP_THREADS), 0, s,
                             a));

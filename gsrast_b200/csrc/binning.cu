@@ -423,6 +423,7 @@ int launch_duplicate_sorted(int P, int grid_x, const uint32_t* sorted_ids, const
     if (P <= 0) return 0;
     if (tile_bits < 1 || tile_bits > 32) return GSR_ERR_INVALID_ARG;
     const int blocks = num_dup_blocks(P);
+    GSR_CARVEOUT(duplicate_sorted_kernel, "DUP", -1);
     duplicate_sorted_kernel<<<blocks, PRE_THREADS, 0, s>>>(P, grid_x, sorted_ids,
                                                            reinterpret_cast<const uint2*>(sorted_rects), block_offsets,
                                                            keys32_out, vals_out, hist, tile_bits, n_sorted);

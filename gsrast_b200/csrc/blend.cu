@@ -167,6 +167,14 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
 //   [0] x, y, a', b'      (conic pre-scaled by log2(e): power*log2(e) = a' dx^2 + c' dy^2 + b' dx dy)
 //   [1] c', opacity, r, g
 //   [2] b, -, -, -
+#ifndef GSR_BLEND_BATCH
+#define GSR_BLEND_BATCH 128   // splats staged per round by the culled kernel (<= BLEND_THREADS, multiple of 32)
+#endif
+constexpr int CBATCH = GSR_BLEND_BATCH;
+static_assert(CBATCH <= BLEND_THREADS && CBATCH % 32 == 0, "one staging thread per splat of a batch");
+#ifndef GSR_BLEND_CARVEOUT
+#define GSR_BLEND_CARVEOUT 25   // 64 KB of shared memory: five 9.4 KB CTAs fit, the rest stays L1 for the gathers
+#endif
 #ifndef GSR_BLEND_MINB
 #define GSR_BLEND_MINB 5
 #endif
@@ -176,9 +184,9 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
 __device__ unsigned long long g_blend_stats[4];
 #endif
 __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_kernel(const BlendParams p) {
-    __shared__ float4 s_splat[BATCH * 3];
-    __shared__ unsigned char s_mask[BATCH];                     // bit w: splat can reach warp w's 8x4 sub-rectangle
-    __shared__ unsigned short s_list[BLEND_THREADS / 32][BATCH]; // per warp: byte offsets (48 * staged index) of its candidates
+    __shared__ float4 s_splat[CBATCH * 3];
+    __shared__ unsigned char s_mask[CBATCH];                     // bit w: splat can reach warp w's 8x4 sub-rectangle
+    __shared__ unsigned short s_list[BLEND_THREADS / 32][CBATCH]; // per warp: byte offsets (48 * staged index) of its candidates
 
     const int tile = p.tile_order ? (int)__ldg(p.tile_order + blockIdx.x) : (int)blockIdx.x;
     const int tile_x = tile % p.grid_x, tile_y = tile / p.grid_x;
@@ -204,7 +212,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
     gsr_pdl_wait();
     const uint2 range = reinterpret_cast<const uint2*>(p.ranges)[tile];
     const int total = (int)(range.y - range.x);
-    const int rounds = (total + BATCH - 1) / BATCH;
+    const int rounds = (total + CBATCH - 1) / CBATCH;
 
     // pixels outside the image start "terminated" (negative T, see the inner loop)
     float T = inside ? 1.0f : -1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
@@ -216,7 +224,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
     float2 n_xy = make_float2(0.f, 0.f);
     float4 n_co = make_float4(0.f, 0.f, 0.f, 0.f);
     float n_c0 = 0.f, n_c1 = 0.f, n_c2 = 0.f;
-    if (tid < total) {
+    const bool stager = tid < CBATCH;  // thread t stages splat t of every batch
+    if (stager && tid < total) {
         const uint32_t id = __ldg(p.point_list + range.x + tid);
         n_xy = __ldg(reinterpret_cast<const float2*>(p.means2D) + id);
         n_co = __ldg(reinterpret_cast<const float4*>(p.conic_opacity) + id);
@@ -229,19 +238,19 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
 #ifdef GSR_BLEND_STATS
         if (tid == 0) atomicAdd(&g_blend_stats[0], 1ull);
 #endif
-        const int progress = r * BATCH + tid;
+        const int progress = r * CBATCH + tid;
         uint32_t m = 0;
         const float2 xy = n_xy;
         const float4 co = n_co;
         const float cr = n_c0, cg = n_c1, cb = n_c2;
-        if (progress + BATCH < total) {
-            const uint32_t id = __ldg(p.point_list + range.x + progress + BATCH);
+        if (stager && progress + CBATCH < total) {
+            const uint32_t id = __ldg(p.point_list + range.x + progress + CBATCH);
             n_xy = __ldg(reinterpret_cast<const float2*>(p.means2D) + id);
             n_co = __ldg(reinterpret_cast<const float4*>(p.conic_opacity) + id);
             const float* col = p.colors + (size_t)id * 3;
             n_c0 = __ldg(col); n_c1 = __ldg(col + 1); n_c2 = __ldg(col + 2);
         }
-        if (progress < total) {
+        if (stager && progress < total) {
             const float a = co.x, b = co.y, c = co.z, o = co.w;
             s_splat[3 * tid + 0] = make_float4(xy.x, xy.y, -0.5f * LOG2E * a, -LOG2E * b);
             s_splat[3 * tid + 1] = make_float4(-0.5f * LOG2E * c, o, cr, cg);
@@ -283,14 +292,14 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
                 }
             }
         }
-        s_mask[tid] = (unsigned char)m;
+        if (stager) s_mask[tid] = (unsigned char)m;
         __syncthreads();
 
         if (!warp_done) {
             // this warp's candidates of the batch, in order
             int n = 0;
 #pragma unroll
-            for (int c0 = 0; c0 < BATCH; c0 += 32) {
+            for (int c0 = 0; c0 < CBATCH; c0 += 32) {
                 const bool mine = (s_mask[c0 + lane] >> warp) & 1u;
                 const unsigned bits = __ballot_sync(0xffffffffu, mine);
                 if (mine) my_list[n + __popc(bits & lane_lt)] = (unsigned short)((c0 + lane) * 48);
@@ -336,7 +345,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
                     break;
                 }
             }
-            if (last_off != 0xffffffffu) last = (uint32_t)(r * BATCH + 1) + last_off / 48u;
+            if (last_off != 0xffffffffu) last = (uint32_t)(r * CBATCH + 1) + last_off / 48u;
         }
     }
 #ifdef GSR_BLEND_STATS
@@ -347,7 +356,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
         __syncthreads();
         atomicMax(&s_maxlast, last);
         __syncthreads();
-        if (tid == 0) atomicAdd(&g_blend_stats[3], (unsigned long long)((s_maxlast + BATCH - 1) / BATCH));
+        if (tid == 0) atomicAdd(&g_blend_stats[3], (unsigned long long)((s_maxlast + CBATCH - 1) / CBATCH));
     }
 #endif
     T = fabsf(T);
@@ -393,8 +402,10 @@ int launch_blend(const BlendParams& p, bool simple, cudaStream_t s) {
     cudaError_t e;
     if (simple)
         e = launch_pdl(blend_simple_kernel, dim3(tiles), dim3(BLEND_THREADS), 0, s, p);
-    else
+    else {
+        GSR_CARVEOUT(blend_culled_kernel, "BLEND", GSR_BLEND_CARVEOUT);
         e = launch_pdl(blend_culled_kernel, dim3(tiles), dim3(BLEND_THREADS), 0, s, p);
+    }
     return e == cudaSuccess ? 1 : -(int)e;
 }
 

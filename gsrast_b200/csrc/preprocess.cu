@@ -480,6 +480,8 @@ int launch_preprocess(const PreprocessParams& p, bool compat, cudaStream_t s) {
     const int vec_means = (p.means_stride == 3) && ((reinterpret_cast<uintptr_t>(p.means3D) & 15) == 0);
     const int vec_scales = p.scales && (p.scales_stride == 3) && ((reinterpret_cast<uintptr_t>(p.scales) & 15) == 0);
     const int vec_sh = p.shs && ((reinterpret_cast<uintptr_t>(p.shs) & 15) == 0) && ((p.M * 3) % 4 == 0);
+    GSR_CARVEOUT(preprocess_kernel<true>, "PRE", -1);
+    GSR_CARVEOUT(preprocess_kernel<false>, "PRE", -1);
     if (compat)
         preprocess_kernel<true><<<blocks, PRE_THREADS, 0, s>>>(p, vec_means, vec_scales, vec_sh);
     else

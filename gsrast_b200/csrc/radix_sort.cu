@@ -516,6 +516,7 @@ int launch_pass(const PassArgs& a, cudaStream_t s) {
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured.fetch_or(bit, std::memory_order_release);
     }
+    GSR_CARVEOUT((onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS, ITEMS, DROP>), "SORT", -1);
     GSR_CUDA_TRY(launch_pdl(onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS, ITEMS, DROP>,
                             dim3((unsigned)num_sort_tiles(a.n, ITEMS)), dim3(SORT_THREADS), smem, s, a));
     return 1;

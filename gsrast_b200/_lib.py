@@ -97,7 +97,7 @@ EXPORTS = (
     "gsr_get_higher_msb", "gsr_sort_pairs_temp_bytes", "gsr_sort_pairs", "gsr_identify_tile_ranges",
     "gsr_error_string", "gsr_version",
     "gsr_renderer_create", "gsr_renderer_destroy", "gsr_renderer_render", "gsr_renderer_render_host",
-    "gsr_renderer_last_times", "gsr_repack_gsrast_scene",
+    "gsr_renderer_last_times", "gsr_repack_gsrast_scene", "gsr_ply_count", "gsr_ply_load",
 )
 
 _lib = None
@@ -162,6 +162,10 @@ def lib():
                                            C.c_void_p]
     L.gsr_renderer_last_times.restype = C.c_int
     L.gsr_renderer_last_times.argtypes = [C.c_void_p, C.POINTER(StageTimes)]
+    L.gsr_ply_count.restype = C.c_int
+    L.gsr_ply_count.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
+    L.gsr_ply_load.restype = C.c_int
+    L.gsr_ply_load.argtypes = [C.c_char_p, C.c_int] + [C.c_void_p] * 7
     L.gsr_repack_gsrast_scene.restype = C.c_int
     L.gsr_repack_gsrast_scene.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p]

@@ -548,6 +548,9 @@ const char* gsr_error_string(int code) {
         case GSR_ERR_ALLOC_FAILED: return "gsrast_b200: scratch allocator returned NULL";
         case GSR_ERR_TOO_MANY_PAIRS: return "gsrast_b200: num_rendered >= 2^30";
         case GSR_ERR_SORT_STALLED: return "gsrast_b200: radix sort look-back watchdog tripped";
+        case GSR_ERR_PLY_OPEN: return "gsrast_b200: cannot open the .ply file";
+        case GSR_ERR_PLY_FORMAT: return "gsrast_b200: .ply header has no vertex count on line 3 or no end_header";
+        case GSR_ERR_PLY_TRUNCATED: return "gsrast_b200: .ply body is shorter than the header's vertex count";
         default: return cudaGetErrorString(static_cast<cudaError_t>(-code));
     }
 }

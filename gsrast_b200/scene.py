@@ -162,6 +162,32 @@ def write_ply(path: str, scene: SplatScene) -> None:
         f.write(rec.tobytes())
 
 
+def load_ply_native(path: str) -> SplatScene:
+    """The same staging through the library's host loader (gsr_ply_count / gsr_ply_load, csrc/ply.cu) — what a C++
+    host calls instead of SplatData::loadFromSplatsPly (SplatData.cpp:114-156).  Raises on any GSR_ERR_PLY_* code."""
+    import ctypes as C
+
+    from . import _lib
+
+    L = _lib.lib()
+    n = C.c_int(0)
+    rc = L.gsr_ply_count(path.encode(), C.byref(n))
+    if rc < 0:
+        raise ValueError("%s (%s)" % (L.gsr_error_string(rc).decode(), path))
+    P = n.value
+    means = np.empty((P, 3), np.float32); scales = np.empty((P, 3), np.float32); rot = np.empty((P, 4), np.float32)
+    opac = np.empty(P, np.float32); shs = np.empty((P, 16, 3), np.float32)
+    bbox = np.zeros(6, np.float32); center = np.zeros(3, np.float32)
+    fp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = L.gsr_ply_load(path.encode(), P, fp(means), fp(scales), fp(rot), fp(opac), fp(shs), fp(bbox), fp(center))
+    if rc < 0:
+        raise ValueError("%s (%s)" % (L.gsr_error_string(rc).decode(), path))
+    sc = SplatScene(means, scales, rot, opac, shs, None, 3, 16)
+    sc.bbox = bbox.reshape(2, 3)
+    sc.center = center
+    return sc
+
+
 def read_ply(path: str) -> SplatScene:
     """SplatData::loadFromSplatsPly + loadFromPly activation, returning contract layouts."""
     with open(path, "rb") as f:

@@ -44,6 +44,9 @@ typedef char* (*gsr_alloc_fn)(size_t bytes, void* user);
 #define GSR_ERR_ALLOC_FAILED (-1001)   /* an allocator callback returned NULL */
 #define GSR_ERR_TOO_MANY_PAIRS (-1002) /* num_rendered >= 2^30: beyond the sort's look-back counters */
 #define GSR_ERR_SORT_STALLED (-1003)   /* internal watchdog tripped (never expected) */
+#define GSR_ERR_PLY_OPEN (-1004)       /* the file cannot be opened ("Bad PLY reader", SplatData.cpp:120-124) */
+#define GSR_ERR_PLY_FORMAT (-1005)     /* no vertex count on the third header line / no end_header */
+#define GSR_ERR_PLY_TRUNCATED (-1006)  /* fewer than P records in the body ("Reader is EOF?", SplatData.cpp:146-152) */
 
 /* Replaces CudaRasterizer::Rasterizer::forward (deps/diff-gaussian-rasterization, absent
  * submodule; call shape at apps/gsrast/GSGaussians.cpp:179-206) — identical argument order
@@ -234,6 +237,17 @@ int gsr_renderer_last_times(void* renderer, gsr_stage_times* out);
  * then f_rest[c*15+k-1]) into the contract layout (float3, sh[k][c]).  Any pair may be NULL. */
 int gsr_repack_gsrast_scene(int P, const float* means4, const float* scales4, const float* shs_raw, float* means3,
                             float* scales3, float* shs, void* stream);
+
+/* Scene staging from the .ply the viewer loads (HOST code, no GPU needed): replaces SplatData::loadFromSplatsPly +
+ * the activation loop (apps/gsrast/SplatData.cpp:114-156, :48-58; record layout SplatData.hpp:17-25) and writes the
+ * rasterizer's contract layout directly — means3D[P][3], scales[P][3] = exp, rotations[P][4] = normalised (w,x,y,z),
+ * opacities[P] = sigmoid, shs[P][16][3] re-interleaved from the file's f_dc[3], f_rest[c*15+k-1] order.
+ * gsr_ply_count reads the header only.  gsr_ply_load fills caller-owned HOST arrays sized for `capacity` Gaussians
+ * (any output may be NULL), optionally the bounding box (min[3], max[3]) and the mean position the viewer uses to
+ * place its camera (GSRastWindow.cpp:26-36), and returns the number of Gaussians read or a GSR_ERR_PLY_* code. */
+int gsr_ply_count(const char* path, int* num_gaussians);
+int gsr_ply_load(const char* path, int capacity, float* means3D, float* scales, float* rotations, float* opacities,
+                 float* shs, float* bbox_min_max, float* center);
 
 const char* gsr_error_string(int code);
 int gsr_version(void);

@@ -7,6 +7,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 
 from gsrast_b200 import camera as Cm
 from gsrast_b200 import scene as S
@@ -59,6 +60,42 @@ def test_ply_round_trip(tmp_path):
     raw = S.contract_sh_to_ply_order(sc.shs)
     assert raw[5, 3 + 1 * 15 + (4 - 1)] == sc.shs[5, 4, 1]
     assert np.array_equal(S.ply_order_to_contract_sh(raw), sc.shs)
+
+
+def test_native_ply_loader_matches_splatdata_semantics(tmp_path):
+    """gsr_ply_count / gsr_ply_load (csrc/ply.cu, host code of the C ABI) against the numpy restatement of
+    SplatData::loadFromSplatsPly + activation (SplatData.cpp:114-156, 48-58), and its three error paths."""
+    from gsrast_b200 import _lib
+
+    sc, _ = S.make_config_scene("C1", P=20_001)  # > one 16384-record read chunk
+    path = str(tmp_path / "data.ply")
+    S.write_ply(path, sc)
+    ref = S.read_ply(path)
+    nat = S.load_ply_native(path)
+    assert nat.P == ref.P == 20_001
+    assert np.array_equal(nat.means3D, ref.means3D) and np.array_equal(nat.shs, ref.shs)
+    assert np.allclose(nat.scales, ref.scales, rtol=2e-7) and np.allclose(nat.opacities, ref.opacities, atol=2e-7)
+    assert np.allclose(nat.rotations, ref.rotations, atol=2e-7)
+    assert np.allclose(nat.bbox[0], ref.means3D.min(0)) and np.allclose(nat.bbox[1], ref.means3D.max(0))
+    assert np.allclose(nat.center, ref.means3D.astype(np.float64).mean(0), atol=1e-5)
+    L = _lib.lib()
+    # missing file, header without a count on line 3, truncated body (SplatData.cpp:120-124, 146-152)
+    with pytest.raises(ValueError, match="cannot open"):
+        S.load_ply_native(str(tmp_path / "nope.ply"))
+    bad = tmp_path / "bad.ply"
+    bad.write_bytes(b"ply\nformat binary_little_endian 1.0\ncomment nothing here\nend_header\n")
+    with pytest.raises(ValueError, match="vertex count"):
+        S.load_ply_native(str(bad))
+    raw = open(path, "rb").read()
+    cut = tmp_path / "cut.ply"
+    cut.write_bytes(raw[:-4000])
+    with pytest.raises(ValueError, match="shorter"):
+        S.load_ply_native(str(cut))
+    import ctypes as C
+    n = C.c_int(-1)
+    assert L.gsr_ply_count(path.encode(), C.byref(n)) == 0 and n.value == 20_001
+    assert L.gsr_ply_load(path.encode(), 5, None, None, None, None, None, None, None) == _lib.ERR_INVALID_ARG  # capacity
+    assert L.gsr_ply_load(path.encode(), 20_001, None, None, None, None, None, None, None) == 20_001  # all outputs optional
 
 
 def test_shard_views_partition():

@@ -25,6 +25,36 @@ def pack_cameras(cameras) -> np.ndarray:
     return np.ascontiguousarray(np.stack([c.packed() for c in cameras]).astype(np.float32))
 
 
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin this process (one per GPU) to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host
+    buffer is allocated: first-touch then places the frame staging memory next to the GPU's PCIe root, which is what
+    the device->host frame copies of `render_host` stream into.  Best effort: returns {"node": n, "cpus": k} or
+    {"skipped": why} (no sysfs, single node, cgroup without those CPUs) and never raises."""
+    import os
+
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return {"skipped": "numa_node = -1"}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return {"skipped": "node %d has no CPU in this process's affinity mask" % node}
+        os.sched_setaffinity(0, allowed)
+        return {"node": node, "cpus": len(allowed)}
+    except Exception as ex:  # noqa: BLE001 - placement is an optimisation, never an error
+        return {"skipped": "%s: %s" % (type(ex).__name__, ex)}
+
+
 def shard_views(n_views: int, rank: int, world_size: int) -> list[int]:
     """Round-robin assignment view v -> rank v % world_size (balanced to within one view)."""
     return list(range(rank, n_views, world_size))
@@ -116,14 +146,10 @@ def gather_frames(local_frames: torch.Tensor, n_views: int, rank: int, world_siz
     send = send.contiguous()
     if world_size == 1:
         return send[:n_views]
-    recv = [torch.empty_like(send) for _ in range(world_size)] if rank == dst else None
-    dist.gather(send, recv, dst=dst, group=group)
+    # one [world, per, ...] landing buffer; view v lives at [v % world, v // world] (round-robin shards), so the
+    # view-ordered batch is its transpose — one strided device copy instead of a per-rank index scatter
+    buf = torch.empty((world_size,) + shape, dtype=send.dtype, device=send.device) if rank == dst else None
+    dist.gather(send, list(buf.unbind(0)) if rank == dst else None, dst=dst, group=group)
     if rank != dst:
         return None
-    out = torch.empty((n_views,) + tuple(local_frames.shape[1:]), dtype=local_frames.dtype,
-                      device=local_frames.device)
-    for r in range(world_size):
-        idx = shard_views(n_views, r, world_size)
-        if idx:
-            out[idx] = recv[r][: len(idx)]
-    return out
+    return buf.transpose(0, 1).reshape((per * world_size,) + shape[1:])[:n_views]

@@ -15,6 +15,7 @@ ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_void_p)
 
 FLAG_GSRAST_COMPAT = 0x1
 FLAG_BLEND_SIMPLE = 0x2
+FLAG_LEAN_STATE = 0x8
 FLAG_RADIX_BINNING = 0x4
 
 ERR_INVALID_ARG = -1000

@@ -176,7 +176,7 @@ static_assert(CBATCH <= BLEND_THREADS && CBATCH % 32 == 0, "one staging thread p
 #define GSR_BLEND_CARVEOUT 25   // 64 KB of shared memory: five 9.4 KB CTAs fit, the rest stays L1 for the gathers
 #endif
 #ifndef GSR_BLEND_MINB
-#define GSR_BLEND_MINB 5
+#define GSR_BLEND_MINB 6   // 40 registers (12 B of spills outside the candidate loop): 48 resident warps, blend -2.6 %
 #endif
 #ifdef GSR_BLEND_STATS
 // diagnostics build only (tools/blend_stats.py): [0] tile-rounds staged, [1] warp-rounds that walked a list,

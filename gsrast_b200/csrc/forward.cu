@@ -280,6 +280,7 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         pp.prefiltered = a->prefiltered;
         pp.radii = radii; pp.rects = a->rects; pp.depths = geom.depths; pp.clamped = geom.clamped;
         pp.means2D = geom.means2D; pp.cov3D = geom.cov3D; pp.conic_opacity = geom.conic_opacity;
+        if (a->flags & GSR_FLAG_LEAN_STATE) { pp.cov3D = nullptr; pp.clamped = nullptr; }
         pp.rgb = geom.rgb; pp.tiles_touched = geom.tiles_touched; pp.block_sums = geom.block_sums;
         pp.depth_keys = geom.depth_keys; pp.tile_rects = geom.tile_rects;
         pp.coarse_block_sums = bin_mode ? geom.coarse_block_sums : nullptr;

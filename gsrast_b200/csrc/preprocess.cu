@@ -184,6 +184,8 @@ __global__ void __launch_bounds__(PRE_THREADS, 6) preprocess_kernel(const Prepro
         // Only for centres on or near the screen (a hint: an off-screen centre with a huge radius just misses).
         if (!COMPAT && alive && p.colors_precomp == nullptr && fabsf(prx) < 1.25f && fabsf(pry) < 1.25f) {
             const char* shp = reinterpret_cast<const char*>(p.shs + (size_t)idx * p.M * 3);
+            // (cp.async.bulk.prefetch.L2 of exactly the block's 192 bytes was tried instead of two line prefetches:
+            // preprocess 0.169 -> 0.190 ms, profiles/r01f_ab.txt)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(shp));
             if (p.M * 12 > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(shp + 128));
         }
@@ -264,10 +266,12 @@ __global__ void __launch_bounds__(PRE_THREADS, 6) preprocess_kernel(const Prepro
                     c[4] = dot3(a01, a02, a11, a12, a21, a22);  // sigma[2][1]: c=2, r=1
                     c[5] = dot3(a02, a02, a12, a12, a22, a22);  // sigma[2][2]
                 }
-                float* co = p.cov3D + (size_t)idx * 6;
-                reinterpret_cast<float2*>(co)[0] = make_float2(c[0], c[1]);
-                reinterpret_cast<float2*>(co)[1] = make_float2(c[2], c[3]);
-                reinterpret_cast<float2*>(co)[2] = make_float2(c[4], c[5]);
+                if (p.cov3D) {  // GSR_FLAG_LEAN_STATE drops it: nothing in the forward pass reads it back
+                    float* co = p.cov3D + (size_t)idx * 6;
+                    reinterpret_cast<float2*>(co)[0] = make_float2(c[0], c[1]);
+                    reinterpret_cast<float2*>(co)[1] = make_float2(c[2], c[3]);
+                    reinterpret_cast<float2*>(co)[2] = make_float2(c[4], c[5]);
+                }
             }
 
             // ---- EWA projection (computeCov2D) -----------------------------------------
@@ -360,7 +364,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 6) preprocess_kernel(const Prepro
         if (tiles == 0 && p.colors_precomp == nullptr) {
             float* o = p.rgb + (size_t)idx * 3;
             o[0] = 0.f; o[1] = 0.f; o[2] = 0.f;
-            if (!COMPAT) {
+            if (!COMPAT && p.clamped) {
                 unsigned char* cl = p.clamped + (size_t)idx * 3;
                 cl[0] = 0; cl[1] = 0; cl[2] = 0;
             }
@@ -449,7 +453,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 6) preprocess_kernel(const Prepro
                 acc2 = fadd(acc2, __shfl_xor_sync(0xffffffffu, acc2, 2));
                 if (act && q < 3) {  // lane q writes channel q: 12 contiguous bytes per Gaussian across 3 lanes
                     const float v = fadd(q == 0 ? acc0 : (q == 1 ? acc1 : acc2), 0.5f);
-                    p.clamped[(size_t)gidx * 3 + q] = v < 0.f;
+                    if (p.clamped) p.clamped[(size_t)gidx * 3 + q] = v < 0.f;
                     p.rgb[(size_t)gidx * 3 + q] = fmaxf(v, 0.f);
                 }
             }

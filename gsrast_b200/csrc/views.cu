@@ -141,7 +141,10 @@ int render_one(Renderer* r, Lane& l, const float* cam36, float tan_fovx, float t
         a.rects = l.rects;
     }
     a.stream = l.stream;
-    a.flags = r->flags;
+#ifndef GSR_RENDERER_LEAN
+#define GSR_RENDERER_LEAN 1
+#endif
+    a.flags = r->flags | (GSR_RENDERER_LEAN ? GSR_FLAG_LEAN_STATE : 0u);  // the lane's scratch is private: nobody can map cov3D / clamped
     a.timings = times;
     return forward_impl(&a, &l.slot);
 }

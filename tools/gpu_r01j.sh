@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-1j evidence: GPU tests, smoke, contract bench (CPU + reference-GPU legs), reference arm, C1/C3/C5 lines,
+# Round-1 evidence (run as r01j, r01l): GPU tests, smoke, contract bench (CPU + reference-GPU legs), reference arm, C1/C3/C5 lines,
 # launch list of the bench command, full captures of the hot kernels.
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q --timeout 900 2>&1 | tail -15 > gpurun_out/pytest_gpu.log

@@ -559,7 +559,7 @@ def main():
             "e2e": {"value": total_frames / (e2e_ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": 144,
                     "d2h_bytes_per_step": frame_bytes, "ms_per_step": e2e_ms / K, "checksum": checksum,
                     "views_per_call": nhost},
-            "gpu_launches": launches_per_frame * K * 1,
+            "gpu_launches": launches_per_frame * K * world,
             "clocks": clocks, "roofline": roof, "stages": stages,
         }
         if cpu:

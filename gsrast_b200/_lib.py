@@ -99,6 +99,7 @@ EXPORTS = (
     "gsr_error_string", "gsr_version",
     "gsr_renderer_create", "gsr_renderer_destroy", "gsr_renderer_render", "gsr_renderer_render_host",
     "gsr_renderer_last_times", "gsr_repack_gsrast_scene", "gsr_ply_count", "gsr_ply_load",
+    "gsr_renderer_render_host_u8", "gsr_frames_to_u8",
 )
 
 _lib = None
@@ -163,6 +164,11 @@ def lib():
                                            C.c_void_p]
     L.gsr_renderer_last_times.restype = C.c_int
     L.gsr_renderer_last_times.argtypes = [C.c_void_p, C.POINTER(StageTimes)]
+    L.gsr_renderer_render_host_u8.restype = C.c_int
+    L.gsr_renderer_render_host_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p,
+                                              C.c_void_p]
+    L.gsr_frames_to_u8.restype = C.c_int
+    L.gsr_frames_to_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.gsr_ply_count.restype = C.c_int
     L.gsr_ply_count.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
     L.gsr_ply_load.restype = C.c_int

@@ -53,6 +53,7 @@ struct Lane {
     // host-output rendering only: two frame buffers per lane, drained by the lane's own copy stream, so the
     // lane renders its next view while the previous frame travels to the host
     float* frame_dev[2] = {nullptr, nullptr};  // [3*H*W] each
+    unsigned char* frame_u8[2] = {nullptr, nullptr};  // [3*H*W] each, 8-bit delivery only
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t rendered[2] = {nullptr, nullptr};
     cudaEvent_t copied[2] = {nullptr, nullptr};
@@ -99,6 +100,7 @@ void lane_destroy(Lane& l) {
     if (l.copy_stream) cudaStreamSynchronize(l.copy_stream);
     for (int b = 0; b < 2; ++b) {
         if (l.frame_dev[b]) cudaFree(l.frame_dev[b]);
+        if (l.frame_u8[b]) cudaFree(l.frame_u8[b]);
         if (l.rendered[b]) cudaEventDestroy(l.rendered[b]);
         if (l.copied[b]) cudaEventDestroy(l.copied[b]);
     }
@@ -147,6 +149,31 @@ int render_one(Renderer* r, Lane& l, const float* cam36, float tan_fovx, float t
     a.flags = r->flags | (GSR_RENDERER_LEAN ? GSR_FLAG_LEAN_STATE : 0u);  // the lane's scratch is private: nobody can map cov3D / clamped
     a.timings = times;
     return forward_impl(&a, &l.slot);
+}
+
+// float frame -> 8 bits per channel, same planar [3][H][W] layout: round(clamp(x, 0, 1) * 255), what the viewer's RGBA8
+// framebuffer and its screenshot path (apps/gsrast/Inspector.cpp:222-257) end up holding.  16 bytes in, 4 bytes out per thread.
+__global__ void quantize_u8_kernel(const size_t n4, const float4* __restrict__ in, uchar4* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = in[i];
+    out[i] = make_uchar4((unsigned char)__float2int_rn(__saturatef(v.x) * 255.0f),
+                         (unsigned char)__float2int_rn(__saturatef(v.y) * 255.0f),
+                         (unsigned char)__float2int_rn(__saturatef(v.z) * 255.0f),
+                         (unsigned char)__float2int_rn(__saturatef(v.w) * 255.0f));
+}
+__global__ void quantize_u8_tail_kernel(const size_t first, const size_t n, const float* __restrict__ in,
+                                        unsigned char* __restrict__ out) {
+    const size_t i = first + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (unsigned char)__float2int_rn(__saturatef(in[i]) * 255.0f);
+}
+int launch_quantize_u8(const float* in, unsigned char* out, size_t n, cudaStream_t s) {
+    const size_t n4 = n / 4;
+    if (n4) quantize_u8_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(n4, reinterpret_cast<const float4*>(in),
+                                                                           reinterpret_cast<uchar4*>(out));
+    if (n4 * 4 < n) quantize_u8_tail_kernel<<<1, 32, 0, s>>>(n4 * 4, n, in, out);
+    cudaError_t e = cudaPeekAtLastError();
+    return e == cudaSuccess ? 1 : -(int)e;
 }
 
 // vec4 means/scales -> float3; PLY-order SH (f_dc[3], f_rest[c*15+k-1]) -> [16][3] interleaved.
@@ -241,15 +268,16 @@ int gsr_renderer_render(void* h, const float* cameras, int n_views, float tan_fo
 
 // Same, but every frame is copied to HOST memory out_color[n_views][3][H][W] (pinned memory
 // makes the copy asynchronous) while the next view renders; returns after all frames landed.
-int gsr_renderer_render_host(void* h, const float* cameras, int n_views, float tan_fovx, float tan_fovy,
-                             float* out_color_host, int* num_rendered) {
-    Renderer* r = static_cast<Renderer*>(h);
-    if (!r || !cameras || !out_color_host || n_views < 0) return GSR_ERR_INVALID_ARG;
+// u8: frames are quantised on the device first and 8-bit frames travel (a quarter of the bytes).
+static int render_host_impl(Renderer* r, const float* cameras, int n_views, float tan_fovx, float tan_fovy,
+                            void* out_host, bool u8, int* num_rendered) {
+    if (!r || !cameras || !out_host || n_views < 0) return GSR_ERR_INVALID_ARG;
     const size_t frame = (size_t)3 * r->W * r->H;
     for (auto& l : r->lane) {
         if (!l.copy_stream) GSR_CUDA_TRY(cudaStreamCreateWithFlags(&l.copy_stream, cudaStreamNonBlocking));
         for (int b = 0; b < 2; ++b) {
             if (!l.frame_dev[b]) GSR_CUDA_TRY(cudaMalloc(&l.frame_dev[b], frame * sizeof(float)));
+            if (u8 && !l.frame_u8[b]) GSR_CUDA_TRY(cudaMalloc(&l.frame_u8[b], frame));
             if (!l.rendered[b]) GSR_CUDA_TRY(cudaEventCreateWithFlags(&l.rendered[b], cudaEventDisableTiming));
             if (!l.copied[b]) GSR_CUDA_TRY(cudaEventCreateWithFlags(&l.copied[b], cudaEventDisableTiming));
         }
@@ -266,10 +294,18 @@ int gsr_renderer_render_host(void* h, const float* cameras, int n_views, float t
         if (l.copy_pending[b]) GSR_CUDA_TRY(cudaStreamWaitEvent(l.stream, l.copied[b], 0));
         int rc = render_one(r, l, cameras + (size_t)v * CAM_FLOATS, tan_fovx, tan_fovy, l.frame_dev[b], nullptr);
         if (rc < 0) { rc_err = rc; break; }
+        if (u8) {
+            int rq = launch_quantize_u8(l.frame_dev[b], l.frame_u8[b], frame, l.stream);
+            if (rq < 0) { rc_err = rq; break; }
+        }
         GSR_CUDA_TRY(cudaEventRecord(l.rendered[b], l.stream));
         GSR_CUDA_TRY(cudaStreamWaitEvent(l.copy_stream, l.rendered[b], 0));
-        GSR_CUDA_TRY(cudaMemcpyAsync(out_color_host + (size_t)v * frame, l.frame_dev[b], frame * sizeof(float),
-                                     cudaMemcpyDeviceToHost, l.copy_stream));
+        if (u8)
+            GSR_CUDA_TRY(cudaMemcpyAsync(static_cast<unsigned char*>(out_host) + (size_t)v * frame, l.frame_u8[b], frame,
+                                         cudaMemcpyDeviceToHost, l.copy_stream));
+        else
+            GSR_CUDA_TRY(cudaMemcpyAsync(static_cast<float*>(out_host) + (size_t)v * frame, l.frame_dev[b],
+                                         frame * sizeof(float), cudaMemcpyDeviceToHost, l.copy_stream));
         GSR_CUDA_TRY(cudaEventRecord(l.copied[b], l.copy_stream));
         l.copy_pending[b] = true;
         if (num_rendered) num_rendered[v] = rc;
@@ -282,6 +318,23 @@ int gsr_renderer_render_host(void* h, const float* cameras, int n_views, float t
     }
     if (rc_err) return rc_err;
     return (int)(total > 0x7fffffffLL ? 0x7fffffff : total);
+}
+
+int gsr_renderer_render_host(void* h, const float* cameras, int n_views, float tan_fovx, float tan_fovy,
+                             float* out_color_host, int* num_rendered) {
+    return render_host_impl(static_cast<Renderer*>(h), cameras, n_views, tan_fovx, tan_fovy, out_color_host, false,
+                            num_rendered);
+}
+
+int gsr_renderer_render_host_u8(void* h, const float* cameras, int n_views, float tan_fovx, float tan_fovy,
+                                unsigned char* out_color_host, int* num_rendered) {
+    return render_host_impl(static_cast<Renderer*>(h), cameras, n_views, tan_fovx, tan_fovy, out_color_host, true,
+                            num_rendered);
+}
+
+int gsr_frames_to_u8(const float* frames, unsigned char* out, size_t n_values, void* stream) {
+    if (!frames || !out) return GSR_ERR_INVALID_ARG;
+    return launch_quantize_u8(frames, out, n_values, static_cast<cudaStream_t>(stream));
 }
 
 int gsr_renderer_last_times(void* h, gsr_stage_times* out) {

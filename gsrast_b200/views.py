@@ -128,6 +128,28 @@ class ViewRenderer:
         _lib.check(rc)
         return out_host, [int(nr[i]) for i in range(n)]
 
+    def render_host_u8(self, cameras, tan_fovx, tan_fovy, out_host=None):
+        """Same with 8-bit frames (quantised on the device): uint8 [n,3,H,W] in (pinned) host memory."""
+        cams = pack_cameras(cameras)
+        n = cams.shape[0]
+        if out_host is None:
+            out_host = torch.empty((n, 3, self.height, self.width), dtype=torch.uint8).pin_memory()
+        nr = (C.c_int * max(n, 1))()
+        rc = _lib.lib().gsr_renderer_render_host_u8(self._h, cams.ctypes.data, n, float(tan_fovx), float(tan_fovy),
+                                                    out_host.data_ptr(), C.cast(nr, C.c_void_p))
+        _lib.check(rc)
+        return out_host, [int(nr[i]) for i in range(n)]
+
+
+def frames_to_u8(frames: torch.Tensor) -> torch.Tensor:
+    """Device float frames -> uint8, round(clamp(x, 0, 1) * 255), same shape (gsr_frames_to_u8)."""
+    frames = frames.contiguous()
+    out = torch.empty(frames.shape, dtype=torch.uint8, device=frames.device)
+    rc = _lib.lib().gsr_frames_to_u8(frames.data_ptr(), out.data_ptr(), frames.numel(),
+                                     torch.cuda.current_stream(frames.device).cuda_stream)
+    _lib.check(rc)
+    return out
+
 
 def gather_frames(local_frames: torch.Tensor, n_views: int, rank: int, world_size: int, dst: int = 0, group=None):
     """Bring the frames of a round-robin-sharded batch to `dst` in view order.

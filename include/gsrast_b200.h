@@ -234,6 +234,13 @@ int gsr_renderer_render(void* renderer, const float* cameras, int n_views, float
  * k overlaps the render of view k+1); returns once every frame has landed. */
 int gsr_renderer_render_host(void* renderer, const float* cameras, int n_views, float tan_fovx, float tan_fovy,
                              float* out_color_host, int* num_rendered);
+/* 8-bit delivery: frames are quantised on the device — round(clamp(x, 0, 1) * 255), same planar [3][H][W] layout, what
+ * the viewer's RGBA8 framebuffer / screenshot path holds (apps/gsrast/Inspector.cpp:222-257) — and a quarter of the
+ * bytes cross PCIe.  out_color_host: HOST uint8[n_views][3][H][W].  gsr_frames_to_u8 is the bare conversion of any
+ * device float array (n_values elements; `frames` 16-byte aligned). */
+int gsr_renderer_render_host_u8(void* renderer, const float* cameras, int n_views, float tan_fovx, float tan_fovy,
+                                unsigned char* out_color_host, int* num_rendered);
+int gsr_frames_to_u8(const float* frames, unsigned char* out, size_t n_values, void* stream);
 int gsr_renderer_last_times(void* renderer, gsr_stage_times* out);
 
 /* One-shot device repack of the buffers GSRast's viewer uploads (vec4 means / scales,

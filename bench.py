@@ -387,8 +387,24 @@ def main():
     render_e2e(packed[Wm:Wm + K])
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
-    clocks = sampler.stop() if rank == 0 else None
     checksum = float(host_out[0].double().mean())
+
+    # same leg with 8-bit frames (quantised on the device): a quarter of the bytes cross PCIe — reported beside `e2e`,
+    # which stays the fp32 delivery the reference's out_color has
+    host_u8 = torch.empty((nhost, 3, H, W), dtype=torch.uint8).pin_memory()
+
+    def render_e2e_u8(cam_block):
+        for i in range(0, cam_block.shape[0], nhost):
+            blk = cam_block[i:i + nhost]
+            vr.render_host_u8(blk, tanx, tany, out_host=host_u8[: blk.shape[0]])
+
+    render_e2e_u8(packed[:Wm])
+    barrier()
+    t0 = time.perf_counter()
+    render_e2e_u8(packed[Wm:Wm + K])
+    torch.cuda.synchronize()
+    e2e_u8_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---------------- optional NCCL gather of frames to rank 0 -----------------------------
     gather_ms = None
@@ -407,9 +423,9 @@ def main():
         gather_ms = g0.elapsed_time(g1)
 
     if dist is not None:
-        t = torch.tensor([dev_ms, e2e_ms, gather_ms or 0.0], dtype=torch.float64, device=dev)
+        t = torch.tensor([dev_ms, e2e_ms, gather_ms or 0.0, e2e_u8_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_ms, gmax = [float(x) for x in t.cpu()]
+        dev_ms, e2e_ms, gmax, e2e_u8_ms = [float(x) for x in t.cpu()]
         gather_ms = gmax if gather_ms is not None else None
 
     # ---------------- per-stage device times + roofline (rank 0) ----------------------------
@@ -559,6 +575,9 @@ def main():
             "e2e": {"value": total_frames / (e2e_ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": 144,
                     "d2h_bytes_per_step": frame_bytes, "ms_per_step": e2e_ms / K, "checksum": checksum,
                     "views_per_call": nhost},
+            "e2e_u8": {"value": total_frames / (e2e_u8_ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": 144,
+                       "d2h_bytes_per_step": frame_bytes // 4, "ms_per_step": e2e_u8_ms / K,
+                       "note": "gsr_renderer_render_host_u8: frames quantised to 8 bits on the device before the copy"},
             "gpu_launches": launches_per_frame * K * world,
             "clocks": clocks, "roofline": roof, "stages": stages,
         }

@@ -73,3 +73,28 @@ def test_repack_gsrast_scene():
     assert np.array_equal(m3.cpu().numpy(), sc.means3D)
     assert np.array_equal(s3.cpu().numpy(), sc.scales)
     assert np.array_equal(sh.cpu().numpy(), sc.shs)
+
+
+def test_u8_frame_delivery():
+    """gsr_renderer_render_host_u8 / gsr_frames_to_u8: round(clamp(x, 0, 1) * 255) of exactly the float frames, planar
+    layout kept, odd element counts (tail kernel) included."""
+    import torch
+
+    from gsrast_b200.views import ViewRenderer, frames_to_u8
+
+    sc = S.make_config_scene("C2", P=60_000)[0]
+    W, H = 800, 448
+    cams = Cm.orbit_cameras(5, W, H)
+    vr = ViewRenderer.from_scene(sc, W, H, background=(0.25, 1.5, -0.5))  # background outside [0, 1] exercises the clamp
+    host_f, nr_f = vr.render_host(cams, cams[0].tan_fovx, cams[0].tan_fovy)
+    host_u, nr_u = vr.render_host_u8(cams, cams[0].tan_fovx, cams[0].tan_fovy)
+    assert nr_f == nr_u and host_u.dtype == torch.uint8 and tuple(host_u.shape) == (5, 3, H, W)
+    f = host_f.numpy()
+    want = np.rint(np.clip(f, 0.0, 1.0) * np.float32(255.0)).astype(np.uint8)  # rint = round-half-even, like cvt.rni
+    assert np.array_equal(host_u.numpy(), want)
+    assert want.min() == 0 and want.max() == 255
+    # the bare conversion, 4k + 3 elements
+    x = torch.linspace(-0.5, 1.5, 4 * 1000 + 3, device="cuda")
+    got = frames_to_u8(x).cpu().numpy()
+    assert np.array_equal(got, np.rint(np.clip(x.cpu().numpy(), 0.0, 1.0) * np.float32(255.0)).astype(np.uint8))
+    vr.close()

@@ -71,8 +71,11 @@ constexpr float SH_C3_0 = -0.5900435899266435f, SH_C3_1 = 2.890611442640554f, SH
                 SH_C3_3 = 0.3731763325901154f, SH_C3_4 = -0.4570457994644658f, SH_C3_5 = 1.445305721320277f,
                 SH_C3_6 = -0.5900435899266435f;
 
+#ifndef GSR_PRE_MINB
+#define GSR_PRE_MINB 6
+#endif
 template <bool COMPAT>
-__global__ void __launch_bounds__(PRE_THREADS, 6) preprocess_kernel(const PreprocessParams p, const int vec_means,
+__global__ void __launch_bounds__(PRE_THREADS, GSR_PRE_MINB) preprocess_kernel(const PreprocessParams p, const int vec_means,
                                                                  const int vec_scales, const int vec_sh) {
     __shared__ __align__(16) float s_means[PRE_THREADS * 3];
     __shared__ __align__(16) float s_scales[PRE_THREADS * 3];

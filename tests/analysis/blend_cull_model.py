@@ -5,10 +5,10 @@ as the source of the sorted lists).  Compares inner-loop trip counts of three wa
   B  warp = two 4x4 half-warps, one list per half-warp, trips = max of the two
   C  warp = 8x8 pixels, two pixels per thread, one list per warp
 Termination is approximated from the oracle's n_contrib / final_T (a sub-rectangle stops once all of its
-pixels have terminated).  Analysis tool only; nothing in the product imports it."""
+pixels have terminated).  Analysis tool only (lives under tests/ because it drives the oracle); nothing in the product imports it."""
 import sys, os
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from gsrast_b200 import camera, scene
 from oracle import gsr_oracle
 

@@ -49,3 +49,37 @@ def test_cpp_host_matches_ctypes(tmp_path, mode):
     assert list(head[1:4]) == [2, 2, 2]          # one call per allocator per frame, two frames
     assert head[4] == cu["radii"][0]             # Inspector-style field access through fromChunk
     assert np.array_equal(img, cu["out_color"])
+
+
+def test_cpp_views_host_ply_to_u8_frames(tmp_path):
+    """tests/cpp/views_host.cpp: .ply -> gsr_ply_load -> gsr_renderer_create -> gsr_renderer_render_host_u8, all from
+    C++ through the C ABI; frames and num_rendered must equal the ctypes path's on the same cameras."""
+    import torch
+
+    from gsrast_b200.views import ViewRenderer, pack_cameras
+
+    exe = os.path.join(ROOT, "tests", "cpp", "views_host")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.dirname(exe), "views_host"])
+    sc = S.make_config_scene("C1", P=30_000)[0]
+    W, H = 640, 360
+    cams = Cm.orbit_cameras(3, W, H)
+    ply, cam_bin, out_bin = str(tmp_path / "data.ply"), str(tmp_path / "cams.bin"), str(tmp_path / "out.bin")
+    S.write_ply(ply, sc)
+    with open(cam_bin, "wb") as f:
+        np.array([len(cams), W, H], np.int32).tofile(f)
+        np.array([cams[0].tan_fovx, cams[0].tan_fovy], np.float32).tofile(f)
+        pack_cameras(cams).astype(np.float32).tofile(f)
+    out = subprocess.check_output([exe, ply, cam_bin, out_bin], timeout=300).decode()
+    assert "views_host: P=30000 views=3" in out
+    head = np.fromfile(out_bin, np.int32, 2 + len(cams))
+    frames = np.fromfile(out_bin, np.uint8, offset=4 * (2 + len(cams))).reshape(len(cams), 3, H, W)
+    # the same scene as the loader stages it (activation round trip through the file), same cameras, ctypes path
+    staged = S.load_ply_native(ply)
+    vr = ViewRenderer.from_scene(staged, W, H)
+    want, nr = vr.render_host_u8(cams, cams[0].tan_fovx, cams[0].tan_fovy)
+    torch.cuda.synchronize()
+    assert list(head[2:]) == nr and head[0] == sc.P
+    assert np.array_equal(frames, want.numpy())
+    assert frames.max() > 0
+    vr.close()

@@ -150,10 +150,12 @@ __global__ void __launch_bounds__(PRE_THREADS) gather_rects_kernel(const int P, 
             cnt += (rec.y >> 16) * (rec.y & 0xffffu);
         }
     }
-    // (b) thread t owns indices 4t..4t+3 of the block's 1024; 64 threads = one preprocess block
+    // (b) thread t owns indices 4t..4t+3 of the block's 1024; 64 threads = one preprocess block.  Skipped (block
+    // uniform) when the caller does not want point_offsets (GSR_FLAG_LEAN_STATE): nothing in the pipeline reads it.
     const int i0 = blockIdx.x * DUP_GAUSS + 4 * tid;
     uint32_t tt[4] = {0u, 0u, 0u, 0u};
-    if (i0 + 4 <= P) {
+    if (!point_offsets) {
+    } else if (i0 + 4 <= P) {
         const uint4 x = __ldg(reinterpret_cast<const uint4*>(tiles_touched + i0));
         tt[0] = x.x; tt[1] = x.y; tt[2] = x.z; tt[3] = x.w;
     } else {
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(PRE_THREADS) gather_rects_kernel(const int P, 
     const uint32_t wsum = __reduce_add_sync(0xffffffffu, cnt);
     if (lane == 0) s_warp[warp] = wsum;
     __syncthreads();
-    if (i0 < P) {
+    if (point_offsets && i0 < P) {
         uint32_t run = __ldg(block_offsets + (i0 / PRE_THREADS)) + ((warp & 1) ? s_pw[warp - 1] : 0u) + incl - tsum;
         uint32_t o[4];
 #pragma unroll

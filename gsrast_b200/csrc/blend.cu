@@ -175,6 +175,12 @@ static_assert(CBATCH <= BLEND_THREADS && CBATCH % 32 == 0, "one staging thread p
 #ifndef GSR_BLEND_CARVEOUT
 #define GSR_BLEND_CARVEOUT 25   // 64 KB of shared memory: five 9.4 KB CTAs fit, the rest stays L1 for the gathers
 #endif
+// GSR_BLEND_ABS16=1: the per-warp lists hold the 16-bit shared-window ADDRESS of a record instead of its offset, so
+// the candidate loop loads the record straight off the list entry (one IADD less per trip).  Static shared memory of
+// a non-cluster launch sits in the low 64 KB of the window; the kernel traps if that ever does not hold.
+#ifndef GSR_BLEND_ABS16
+#define GSR_BLEND_ABS16 1
+#endif
 #ifndef GSR_BLEND_MINB
 #define GSR_BLEND_MINB 6   // 40 registers (12 B of spills outside the candidate loop): 48 resident warps, blend -2.6 %
 #endif
@@ -209,6 +215,12 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
     float pixf_xo = pixf_x, pixf_yo = pixf_y;
     asm volatile("" : "+r"(splat_base), "+r"(list_base), "+f"(t_min), "+f"(pixf_xo), "+f"(pixf_yo));
 
+#if GSR_BLEND_ABS16
+    if ((splat_base + (uint32_t)(CBATCH * 48)) >> 16) __trap();
+    const uint32_t rec_bias = splat_base;
+#else
+    constexpr uint32_t rec_bias = 0u;
+#endif
     gsr_pdl_wait();
     const uint2 range = reinterpret_cast<const uint2*>(p.ranges)[tile];
     const int total = (int)(range.y - range.x);
@@ -302,7 +314,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
             for (int c0 = 0; c0 < CBATCH; c0 += 32) {
                 const bool mine = (s_mask[c0 + lane] >> warp) & 1u;
                 const unsigned bits = __ballot_sync(0xffffffffu, mine);
-                if (mine) my_list[n + __popc(bits & lane_lt)] = (unsigned short)((c0 + lane) * 48);
+                if (mine) my_list[n + __popc(bits & lane_lt)] = (unsigned short)(rec_bias + (uint32_t)((c0 + lane) * 48));
                 n += __popc(bits);
             }
             __syncwarp();
@@ -319,8 +331,13 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
 #pragma unroll 2
                 for (int i = i0; i < i1; ++i) {
                     const uint32_t off = lds16(list_base + 2u * (uint32_t)i);
-                    const float4 a = lds128(splat_base + off);
-                    const float4 b = lds128(splat_base + off + 16u);
+#if GSR_BLEND_ABS16
+                    const uint32_t rec = off;  // the entry is the record's address
+#else
+                    const uint32_t rec = splat_base + off;
+#endif
+                    const float4 a = lds128(rec);
+                    const float4 b = lds128(rec + 16u);
                     const float dx = a.x - pixf_xo, dy = a.y - pixf_yo;
                     // the three terms are formed separately like the reference's (GSCuda.cu:634): a factored form
                     // saves one FMUL but rounds differently where they cancel (elongated splats far from the centre)
@@ -334,7 +351,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
                     if (ok) {
                         C0 = fmaf(b.z, w, C0);
                         C1 = fmaf(b.w, w, C1);
-                        C2 = fmaf(lds32(splat_base + off + 32u), w, C2);
+                        C2 = fmaf(lds32(rec + 32u), w, C2);
                         T = test_T;
                         last_off = off;
                     }
@@ -345,7 +362,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
                     break;
                 }
             }
-            if (last_off != 0xffffffffu) last = (uint32_t)(r * CBATCH + 1) + last_off / 48u;
+            if (last_off != 0xffffffffu) last = (uint32_t)(r * CBATCH + 1) + (last_off - rec_bias) / 48u;
         }
     }
 #ifdef GSR_BLEND_STATS

@@ -280,10 +280,11 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         pp.prefiltered = a->prefiltered;
         pp.radii = radii; pp.rects = a->rects; pp.depths = geom.depths; pp.clamped = geom.clamped;
         pp.means2D = geom.means2D; pp.cov3D = geom.cov3D; pp.conic_opacity = geom.conic_opacity;
-        if (a->flags & GSR_FLAG_LEAN_STATE) { pp.cov3D = nullptr; pp.clamped = nullptr; }
         pp.rgb = geom.rgb; pp.tiles_touched = geom.tiles_touched; pp.block_sums = geom.block_sums;
         pp.depth_keys = geom.depth_keys; pp.tile_rects = geom.tile_rects;
         pp.coarse_block_sums = bin_mode ? geom.coarse_block_sums : nullptr;
+        const bool lean = (a->flags & GSR_FLAG_LEAN_STATE) != 0;
+        if (lean) { pp.cov3D = nullptr; pp.clamped = nullptr; pp.tiles_touched = nullptr; }
         // all clears of the frame up front, so the kernels behind them form uninterrupted dependent-launch chains
         if (!sort32_prepare(geom.depth_sort_space, (size_t)P, 32, s)) GSR_FAIL(-(int)cudaGetLastError());
         {
@@ -314,8 +315,8 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         GSR_STAGE(launch_sort32(dp, s, sort_timed ? sort_ev : nullptr));
         // tile rects into depth order + scan of the per-block pair counts (same total, other order)
         GSR_STAGE(launch_gather_rects(P, geom.depth_sort_ids[1], geom.tile_rects, geom.sorted_rects,
-                                      geom.sorted_block_sums, geom.tiles_touched, geom.block_sums, geom.point_offsets,
-                                      bin_mode, s, n_depth));
+                                      geom.sorted_block_sums, geom.tiles_touched, geom.block_sums,
+                                      lean ? nullptr : geom.point_offsets, bin_mode, s, n_depth));
         const int ndb = num_dup_blocks(P);
         GSR_STAGE(launch_scan_block_sums(geom.sorted_block_sums, ndb, geom.sorted_block_sums + ndb, nullptr, s));
         tm.mark();  // 3

@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(PRE_THREADS, GSR_PRE_MINB) preprocess_kernel(c
             }
         }
         p.radii[idx] = radius_out;
-        p.tiles_touched[idx] = tiles;
+        if (p.tiles_touched) p.tiles_touched[idx] = tiles;
         // low half of the sort key (GSCuda.cu:466-471); Gaussians that emit nothing sort last
         p.depth_keys[idx] = tiles ? __float_as_uint(depth) : 0xffffffffu;
         reinterpret_cast<uint2*>(p.tile_rects)[idx] = rec;

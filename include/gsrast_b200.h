@@ -39,10 +39,12 @@ typedef char* (*gsr_alloc_fn)(size_t bytes, void* user);
                                        (the path CUB takes in the reference, GSCuda.cu:794-797) instead of the default
                                        bin expansion (sort per 8x8-tile bin, expand each bin into its tiles); same
                                        output bit for bit; also taken automatically for grids of more than 4096 bins */
-#define GSR_FLAG_LEAN_STATE 0x8u    /* do not materialise the two geometry-state fields nothing in the forward pass
-                                       reads, cov3D[6P] and clamped[3P] (27 B/Gaussian of stores; the reference keeps
-                                       them for its Inspector, apps/gsrast/Inspector.cpp:174-188).  gsr_renderer_* sets
-                                       it for its private per-lane scratch; gsr_forward* never does on its own */
+#define GSR_FLAG_LEAN_STATE 0x8u    /* do not materialise the geometry-state fields nothing in this forward pass reads:
+                                       cov3D[6P], clamped[3P], tiles_touched[P] and point_offsets[P] (35 B/Gaussian of
+                                       stores + the 4 B/Gaussian re-read of the index-order scan; the reference keeps them
+                                       for its Inspector and for duplicateWithKeys, apps/gsrast/Inspector.cpp:174-188,
+                                       GSCuda.cu:445).  gsr_renderer_* sets it for its private per-lane scratch;
+                                       gsr_forward* never does on its own */
 
 #define GSR_ERR_INVALID_ARG (-1000)
 #define GSR_ERR_ALLOC_FAILED (-1001)   /* an allocator callback returned NULL */

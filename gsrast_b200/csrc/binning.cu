@@ -206,10 +206,20 @@ __global__ void __launch_bounds__(PRE_THREADS) gather_rects_kernel(const int P, 
 // through shared memory so the stores are fully coalesced and one huge splat cannot serialise a
 // thread.  The digit histograms of the tile passes are counted here (shared-memory atomics, flushed once
 // per block), so the sort never re-reads the keys.
+//
+// FUSED (GSR_FLAG_LEAN_STATE callers, which do not need point_offsets): the kernel also does what gather_rects_kernel
+// and the single-CTA scan behind it do — it gathers the tile rects of its depth ranks itself (`sorted_rects` is then
+// tile_rects indexed by Gaussian id, `coarse` turns them into bin rects) and finds its output offset by decoupled
+// look-back over the pair counts of the blocks before it: `fuse_state` = one 64-bit word per block (count << 2 | flag;
+// flag 1 = this block's count, 2 = inclusive prefix) followed by the ticket counter that hands out block numbers in
+// start order (a block only ever waits for blocks that have started), all zeroed by the caller.
+constexpr unsigned long long FUSE_AGG = 1ull, FUSE_INC = 2ull;
+template <bool FUSED>
 __global__ void __launch_bounds__(PRE_THREADS) duplicate_sorted_kernel(
     const int P_all, const int grid_x, const uint32_t* __restrict__ sorted_ids, const uint2* __restrict__ sorted_rects,
     const uint32_t* __restrict__ block_offsets, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-    uint32_t* __restrict__ hist, const int tile_bits, const uint32_t* __restrict__ n_sorted) {
+    uint32_t* __restrict__ hist, const int tile_bits, const uint32_t* __restrict__ n_sorted, const int coarse,
+    unsigned long long* __restrict__ fuse_state, const int fuse_blocks) {
     __shared__ uint32_t s_excl[DUP_GAUSS + 1];
     // 16-byte aligned: the compiler reads the 8 warp sums with LDS.128, which otherwise straddles s_excl[DUP_GAUSS]
     // (unused lane of the vector, but compute-sanitizer racecheck rightly flags the overlap with its later store)
@@ -223,16 +233,41 @@ __global__ void __launch_bounds__(PRE_THREADS) duplicate_sorted_kernel(
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int passes = (tile_bits + 7) >> 3;
-    const int i0 = blockIdx.x * DUP_GAUSS + DUP_GPT * tid;
     gsr_pdl_wait();
     gsr_pdl_launch_dependents();
+    __shared__ uint32_t s_block;
+    int block = blockIdx.x;
+    if (FUSED) {
+        if (tid == 0) s_block = atomicAdd(reinterpret_cast<uint32_t*>(fuse_state + fuse_blocks), 1u);
+        __syncthreads();
+        block = (int)s_block;
+    }
+    const int i0 = block * DUP_GAUSS + DUP_GPT * tid;
     const int P = n_sorted ? min(P_all, (int)__ldg(n_sorted)) : P_all;  // depth ranks that exist
-    if (blockIdx.x * DUP_GAUSS >= P) return;
+    if (block * DUP_GAUSS >= P) return;  // (fused: nothing before this block ever looks at it)
     // every global load of the block is issued here, before anything waits
-    const uint32_t boff = __ldg(block_offsets + blockIdx.x);
+    uint32_t boff = FUSED ? 0u : __ldg(block_offsets + block);
     uint2 rec[DUP_GPT];
     uint32_t gid[DUP_GPT];
-    if (i0 + DUP_GPT <= P) {
+    if (FUSED) {
+        if (i0 + DUP_GPT <= P) {
+            const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(sorted_ids + i0));
+            gid[0] = g4.x; gid[1] = g4.y; gid[2] = g4.z; gid[3] = g4.w;
+#pragma unroll
+            for (int c = 0; c < DUP_GPT; ++c) rec[c] = __ldg(sorted_rects + gid[c]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < DUP_GPT; ++c) {
+                const bool ok = i0 + c < P;
+                gid[c] = ok ? __ldg(sorted_ids + i0 + c) : 0u;
+                rec[c] = ok ? __ldg(sorted_rects + gid[c]) : make_uint2(0u, 0u);
+            }
+        }
+        if (coarse) {
+#pragma unroll
+            for (int c = 0; c < DUP_GPT; ++c) rec[c] = coarse_rect(rec[c]);
+        }
+    } else if (i0 + DUP_GPT <= P) {
         const uint4 r01 = __ldg(reinterpret_cast<const uint4*>(sorted_rects + i0));
         const uint4 r23 = __ldg(reinterpret_cast<const uint4*>(sorted_rects + i0) + 1);
         const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(sorted_ids + i0));
@@ -268,6 +303,38 @@ __global__ void __launch_bounds__(PRE_THREADS) duplicate_sorted_kernel(
     for (int w = 0; w < PRE_THREADS / 32; ++w) {
         if (w < warp) woff += s_warp[w];
         total += s_warp[w];
+    }
+    if (FUSED) {
+        // decoupled look-back (warp 0): publish this block's count, add up the counts of the blocks before it until one
+        // of them carries an inclusive prefix, publish the own inclusive prefix.  One 64-bit word per block, so count
+        // and flag arrive together; volatile loads + relaxed stores, __threadfence orders nothing else that matters
+        // (the words carry their whole payload).
+        __shared__ uint32_t s_boff;
+        if (warp == 0) {
+            volatile unsigned long long* st = fuse_state;
+            if (lane == 0) st[block] = ((unsigned long long)total << 2) | (block == 0 ? FUSE_INC : FUSE_AGG);
+            uint32_t excl = 0;
+            int look = block - 1;
+            while (look >= 0) {
+                const int j = look - lane;
+                unsigned long long v = FUSE_INC;  // lanes before block 0: an inclusive prefix of zero
+                if (j >= 0) {
+                    do { v = st[j]; } while ((v & 3ull) == 0ull);
+                }
+                const unsigned inc = __ballot_sync(0xffffffffu, (v & 3ull) == FUSE_INC);
+                const int first = inc ? (__ffs((int)inc) - 1) : 32;  // nearest block holding an inclusive prefix
+                const uint32_t part = (lane <= first) ? (uint32_t)(v >> 2) : 0u;
+                excl += __reduce_add_sync(0xffffffffu, part);
+                if (inc) break;
+                look -= 32;
+            }
+            if (lane == 0) {
+                if (block != 0) st[block] = ((unsigned long long)(excl + total) << 2) | FUSE_INC;
+                s_boff = excl;
+            }
+        }
+        __syncthreads();
+        boff = s_boff;
     }
     if (total == 0) return;  // the culled tail of the depth order emits nothing (block-uniform)
     {
@@ -425,10 +492,26 @@ int launch_duplicate_sorted(int P, int grid_x, const uint32_t* sorted_ids, const
     if (P <= 0) return 0;
     if (tile_bits < 1 || tile_bits > 32) return GSR_ERR_INVALID_ARG;
     const int blocks = num_dup_blocks(P);
-    GSR_CARVEOUT(duplicate_sorted_kernel, "DUP", -1);
-    duplicate_sorted_kernel<<<blocks, PRE_THREADS, 0, s>>>(P, grid_x, sorted_ids,
-                                                           reinterpret_cast<const uint2*>(sorted_rects), block_offsets,
-                                                           keys32_out, vals_out, hist, tile_bits, n_sorted);
+    GSR_CARVEOUT(duplicate_sorted_kernel<false>, "DUP", -1);
+    duplicate_sorted_kernel<false><<<blocks, PRE_THREADS, 0, s>>>(
+        P, grid_x, sorted_ids, reinterpret_cast<const uint2*>(sorted_rects), block_offsets, keys32_out, vals_out, hist,
+        tile_bits, n_sorted, 0, nullptr, 0);
+    cudaError_t e = cudaPeekAtLastError();
+    return e == cudaSuccess ? 1 : -(int)e;
+}
+
+size_t duplicate_fused_state_bytes(int P) { return ((size_t)num_dup_blocks(P) + 1) * sizeof(unsigned long long); }
+
+int launch_duplicate_fused(int P, int grid_x, const uint32_t* sorted_ids, const uint32_t* tile_rects, bool coarse,
+                           void* fuse_state, uint32_t* keys32_out, uint32_t* vals_out, uint32_t* hist, int tile_bits,
+                           cudaStream_t s, const uint32_t* n_sorted) {
+    if (P <= 0) return 0;
+    if (tile_bits < 1 || tile_bits > 32 || !fuse_state) return GSR_ERR_INVALID_ARG;
+    const int blocks = num_dup_blocks(P);
+    GSR_CARVEOUT(duplicate_sorted_kernel<true>, "DUP", -1);
+    duplicate_sorted_kernel<true><<<blocks, PRE_THREADS, 0, s>>>(
+        P, grid_x, sorted_ids, reinterpret_cast<const uint2*>(tile_rects), nullptr, keys32_out, vals_out, hist, tile_bits,
+        n_sorted, coarse ? 1 : 0, static_cast<unsigned long long*>(fuse_state), blocks);
     cudaError_t e = cudaPeekAtLastError();
     return e == cudaSuccess ? 1 : -(int)e;
 }

@@ -184,6 +184,10 @@ int gsr_forward_ex(const gsr_forward_args* a) { return gsr::forward_impl(a, null
 
 }  // extern "C"
 
+// GSR_FUSED_DUP=1: lean calls run the fused duplication (gather + look-back + emit in one kernel)
+#ifndef GSR_FUSED_DUP
+#define GSR_FUSED_DUP 0
+#endif
 int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
     HostSlot& slot = slot_in ? *slot_in : g_slot;
     if (!a || !a->geometry_alloc || !a->binning_alloc || !a->image_alloc) return GSR_ERR_INVALID_ARG;
@@ -256,6 +260,7 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
     } while (0)
 
     uint32_t R = 0, Rc = 0;
+    bool fused_dup = false;
     const uint32_t* n_depth = nullptr;  // device: Gaussians the depth sort kept
     tm.mark();  // 0
     if (P > 0) {
@@ -285,6 +290,13 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         pp.coarse_block_sums = bin_mode ? geom.coarse_block_sums : nullptr;
         const bool lean = (a->flags & GSR_FLAG_LEAN_STATE) != 0;
         if (lean) { pp.cov3D = nullptr; pp.clamped = nullptr; pp.tiles_touched = nullptr; }
+        // lean callers need no point_offsets, so the duplication can gather its rects and find its offsets itself
+        // (binning.cu, duplicate_sorted_kernel<true>) instead of running behind gather_rects + a single-CTA scan
+        fused_dup = lean && GSR_FUSED_DUP != 0;
+        if (fused_dup) {
+            cudaError_t ez = cudaMemsetAsync(geom.sorted_block_sums, 0, duplicate_fused_state_bytes(P), s);
+            if (ez != cudaSuccess) GSR_FAIL(-(int)ez);
+        }
         // all clears of the frame up front, so the kernels behind them form uninterrupted dependent-launch chains
         if (!sort32_prepare(geom.depth_sort_space, (size_t)P, 32, s)) GSR_FAIL(-(int)cudaGetLastError());
         {
@@ -314,11 +326,11 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         n_depth = sort32_kept_count(geom.depth_sort_space, (size_t)P, 32);
         GSR_STAGE(launch_sort32(dp, s, sort_timed ? sort_ev : nullptr));
         // tile rects into depth order + scan of the per-block pair counts (same total, other order)
-        GSR_STAGE(launch_gather_rects(P, geom.depth_sort_ids[1], geom.tile_rects, geom.sorted_rects,
+        if (!fused_dup) GSR_STAGE(launch_gather_rects(P, geom.depth_sort_ids[1], geom.tile_rects, geom.sorted_rects,
                                       geom.sorted_block_sums, geom.tiles_touched, geom.block_sums,
                                       lean ? nullptr : geom.point_offsets, bin_mode, s, n_depth));
         const int ndb = num_dup_blocks(P);
-        GSR_STAGE(launch_scan_block_sums(geom.sorted_block_sums, ndb, geom.sorted_block_sums + ndb, nullptr, s));
+        if (!fused_dup) GSR_STAGE(launch_scan_block_sums(geom.sorted_block_sums, ndb, geom.sorted_block_sums + ndb, nullptr, s));
         tm.mark();  // 3
         // the one host round trip: num_rendered decides the binning allocation (GSCuda.cu:772,782)
         e = cudaEventSynchronize(slot.landed);
@@ -364,8 +376,12 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         if (Rc == 0 || Rc > R) GSR_FAIL(GSR_ERR_INVALID_ARG);  // cannot happen: every pair lies in one of its Gaussian's bins
         uint32_t* bin_hist = sort32_prepare(tile_temp, (size_t)Rc, bin_bits, s);
         if (!bin_hist) GSR_FAIL(-(int)cudaGetLastError());
-        GSR_STAGE(launch_duplicate_sorted(P, bins_x, geom.depth_sort_ids[1], geom.sorted_rects, geom.sorted_block_sums,
-                                          k32[0], v32[0], bin_hist, bin_bits, s, n_depth));
+        if (fused_dup)
+            GSR_STAGE(launch_duplicate_fused(P, bins_x, geom.depth_sort_ids[1], geom.tile_rects, /*coarse=*/true,
+                                             geom.sorted_block_sums, k32[0], v32[0], bin_hist, bin_bits, s, n_depth));
+        else
+            GSR_STAGE(launch_duplicate_sorted(P, bins_x, geom.depth_sort_ids[1], geom.sorted_rects, geom.sorted_block_sums,
+                                              k32[0], v32[0], bin_hist, bin_bits, s, n_depth));
         tm.mark();  // 4
         const int out = tile_passes & 1;  // one pass: [0] -> [1]; two: [0] -> [1] -> [0]
         {
@@ -396,8 +412,12 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
     } else {
         uint32_t* tile_hist = sort32_prepare(tile_temp, (size_t)R, tile_bits, s);
         if (!tile_hist) GSR_FAIL(-(int)cudaGetLastError());
-        GSR_STAGE(launch_duplicate_sorted(P, gx, geom.depth_sort_ids[1], geom.sorted_rects, geom.sorted_block_sums, k32[0],
-                                          v32[0], tile_hist, tile_bits, s, n_depth));
+        if (fused_dup)
+            GSR_STAGE(launch_duplicate_fused(P, gx, geom.depth_sort_ids[1], geom.tile_rects, /*coarse=*/false,
+                                             geom.sorted_block_sums, k32[0], v32[0], tile_hist, tile_bits, s, n_depth));
+        else
+            GSR_STAGE(launch_duplicate_sorted(P, gx, geom.depth_sort_ids[1], geom.sorted_rects, geom.sorted_block_sums, k32[0],
+                                              v32[0], tile_hist, tile_bits, s, n_depth));
         tm.mark();  // 4
         {
             Sort32Plan tp;

@@ -87,6 +87,13 @@ int launch_gather_rects(int P, const uint32_t* sorted_ids, const uint32_t* tile_
 int launch_duplicate_sorted(int P, int grid_x, const uint32_t* sorted_ids, const uint32_t* sorted_rects,
                             const uint32_t* block_offsets, uint32_t* keys32_out, uint32_t* vals_out, uint32_t* hist,
                             int tile_bits, cudaStream_t s, const uint32_t* n_sorted = nullptr);
+// Fused form for callers that do not need point_offsets: gathers the rects by id itself (tile_rects; coarse = emit
+// (bin, Gaussian) records) and finds its offsets by decoupled look-back; `fuse_state` = duplicate_fused_state_bytes(P)
+// zeroed bytes.  Replaces launch_gather_rects + the scan of its block sums + launch_duplicate_sorted.
+size_t duplicate_fused_state_bytes(int P);
+int launch_duplicate_fused(int P, int grid_x, const uint32_t* sorted_ids, const uint32_t* tile_rects, bool coarse,
+                           void* fuse_state, uint32_t* keys32_out, uint32_t* vals_out, uint32_t* hist, int tile_bits,
+                           cudaStream_t s, const uint32_t* n_sorted = nullptr);
 // zero_first: clear ranges[num_tiles] here (otherwise the caller has already done it)
 int launch_identify_ranges(const uint64_t* keys, size_t n, uint32_t* ranges, int num_tiles, bool compat,
                            cudaStream_t s, bool zero_first = true);

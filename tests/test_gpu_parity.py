@@ -221,16 +221,18 @@ def test_higher_msb_matches(oracle):
 def test_lean_state_flag_changes_no_output_of_the_pass(oracle):
     """GSR_FLAG_LEAN_STATE (what gsr_renderer_* uses for its private scratch): every output of the forward pass is
     identical; only the geometry-state fields nothing in the pass reads (cov3D, clamped, tiles_touched, point_offsets) are
-    not materialised."""
+    not materialised.  150 k Gaussians = 147 duplication blocks, so a fused duplication's look-back crosses several
+    32-block windows; both binning modes."""
     from gsrast_b200 import _lib
 
-    sc = S.make_config_scene("C1", P=20_000)[0]
-    cam = Cm.default_camera(640, 360)
-    full = run_cuda(sc, cam)
-    lean = run_cuda(sc, cam, flags=_lib.FLAG_LEAN_STATE)
-    assert full["num_rendered"] == lean["num_rendered"] > 0
-    for k in ("radii", "depths", "means2D", "conic_opacity", "rgb", "keys", "values", "ranges", "n_contrib", "final_T",
-              "out_color"):
-        assert np.array_equal(full[k], lean[k]), k
-    vis = full["radii"] > 0
-    assert np.abs(full["cov3D"].reshape(-1, 6)[vis]).max() > 0  # the default call does fill it
+    sc = S.make_config_scene("C2", P=150_000)[0]
+    cam = Cm.default_camera(800, 448)
+    for extra in (0, _lib.FLAG_RADIX_BINNING):
+        full = run_cuda(sc, cam, flags=extra)
+        lean = run_cuda(sc, cam, flags=extra | _lib.FLAG_LEAN_STATE)
+        assert full["num_rendered"] == lean["num_rendered"] > 0
+        for k in ("radii", "depths", "means2D", "conic_opacity", "rgb", "keys", "values", "ranges", "n_contrib",
+                  "final_T", "out_color"):
+            assert np.array_equal(full[k], lean[k]), (extra, k)
+        vis = full["radii"] > 0
+        assert np.abs(full["cov3D"].reshape(-1, 6)[vis]).max() > 0  # the default call does fill it

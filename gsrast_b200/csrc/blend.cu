@@ -173,7 +173,7 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
 constexpr int CBATCH = GSR_BLEND_BATCH;
 static_assert(CBATCH <= BLEND_THREADS && CBATCH % 32 == 0, "one staging thread per splat of a batch");
 #ifndef GSR_BLEND_CARVEOUT
-#define GSR_BLEND_CARVEOUT 25   // 64 KB of shared memory: five 9.4 KB CTAs fit, the rest stays L1 for the gathers
+#define GSR_BLEND_CARVEOUT 25   // 64 KB of shared memory: six 8.3 KB CTAs (+1 KB reserved each) fit, the rest stays L1 for the gathers
 #endif
 // GSR_BLEND_ABS16=1: the per-warp lists hold the 16-bit shared-window ADDRESS of a record instead of its offset, so
 // the candidate loop loads the record straight off the list entry (one IADD less per trip).  Static shared memory of

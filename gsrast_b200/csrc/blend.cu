@@ -346,16 +346,17 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
                     const float w = alpha * T;
                     const float test_T = T - w;  // T*(1-alpha)
                     const bool cand = (p2 <= 0.0f) && (alpha >= ALPHA_MIN);
-                    const bool ok = cand && (test_T >= t_min);
-                    const bool term = cand && !(test_T >= t_min);  // also true again later: idempotent below
+                    const bool pass = test_T >= t_min;
+                    const bool ok = cand && pass;
                     if (ok) {
                         C0 = fmaf(b.z, w, C0);
                         C1 = fmaf(b.w, w, C1);
                         C2 = fmaf(lds32(rec + 32u), w, C2);
-                        T = test_T;
                         last_off = off;
                     }
-                    if (term) T = __uint_as_float(__float_as_uint(T) | 0x80000000u);  // T = -|T|: stop, keep final T
+                    // one select updates T for every candidate: blended -> T(1 - alpha); would fall below t_min -> stop,
+                    // keeping the final T as -|T| (true again for every later candidate: idempotent)
+                    if (cand) T = pass ? test_T : -fabsf(T);
                 }
                 if (__all_sync(0xffffffffu, T <= 0.0f)) {
                     warp_done = true;

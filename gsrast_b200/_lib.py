@@ -17,6 +17,10 @@ FLAG_GSRAST_COMPAT = 0x1
 FLAG_BLEND_SIMPLE = 0x2
 FLAG_LEAN_STATE = 0x8
 FLAG_RADIX_BINNING = 0x4
+FLAG_BLEND_COUNT = 0x10
+FLAG_KEEP_STATE = 0x20
+BLEND_COUNTERS = ("tile_rounds", "warp_rounds", "candidates_listed", "warp_trips", "pairs_live", "pairs_passed",
+                  "pairs_blended", "splats_staged")
 
 ERR_INVALID_ARG = -1000
 ERR_ALLOC_FAILED = -1001
@@ -31,11 +35,13 @@ class StageTimes(C.Structure):
                 ("sort_hist_ms", C.c_float), ("sort_pass_ms", C.c_float * 8),
                 ("depth_sort_ms", C.c_float), ("depth_passes", C.c_int),
                 ("expand_ms", C.c_float), ("num_coarse", C.c_int), ("binning_mode", C.c_int),
-                ("expand_count_ms", C.c_float), ("expand_fill_ms", C.c_float)]
+                ("expand_count_ms", C.c_float), ("expand_fill_ms", C.c_float),
+                ("blend_counters", C.c_ulonglong * 8)]
 
     def as_dict(self):
         d = {n: getattr(self, n) for n, _ in self._fields_}
         d["sort_pass_ms"] = [float(x) for x in self.sort_pass_ms][: max(self.sort_passes, 0)]
+        d["blend_counters"] = {n: int(self.blend_counters[i]) for i, n in enumerate(BLEND_COUNTERS)}
         return d
 
 
@@ -81,7 +87,7 @@ class GeometryState(C.Structure):
 
 
 class ImageState(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("ranges", "n_contrib", "accum_alpha", "tile_order")]
+    _fields_ = [(n, C.c_void_p) for n in ("ranges", "n_contrib", "accum_alpha", "tile_order", "blend_counters")]
 
 
 class BinningState(C.Structure):
@@ -99,7 +105,7 @@ EXPORTS = (
     "gsr_error_string", "gsr_version",
     "gsr_renderer_create", "gsr_renderer_destroy", "gsr_renderer_render", "gsr_renderer_render_host",
     "gsr_renderer_last_times", "gsr_repack_gsrast_scene", "gsr_ply_count", "gsr_ply_load",
-    "gsr_renderer_render_host_u8", "gsr_frames_to_u8",
+    "gsr_renderer_render_host_u8", "gsr_frames_to_u8", "gsr_renderer_map_geometry_state", "gsr_renderer_num_lanes",
 )
 
 _lib = None
@@ -169,6 +175,10 @@ def lib():
                                               C.c_void_p]
     L.gsr_frames_to_u8.restype = C.c_int
     L.gsr_frames_to_u8.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.gsr_renderer_map_geometry_state.restype = C.c_int
+    L.gsr_renderer_map_geometry_state.argtypes = [C.c_void_p, C.c_int, C.POINTER(GeometryState)]
+    L.gsr_renderer_num_lanes.restype = C.c_int
+    L.gsr_renderer_num_lanes.argtypes = []
     L.gsr_ply_count.restype = C.c_int
     L.gsr_ply_count.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
     L.gsr_ply_load.restype = C.c_int

@@ -33,8 +33,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(uint32_t*
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
     __shared__ uint32_t s_carry;
     __shared__ uint32_t s_total2;
+    __shared__ unsigned long long s_total64;  // the same total in 64 bits: tells a wrapped 32-bit sum from a small one
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { s_carry = 0; s_total2 = 0; }
+    unsigned long long my64 = 0;
+    if (tid == 0) { s_carry = 0; s_total2 = 0; s_total64 = 0; }
     gsr_pdl_wait();
     gsr_pdl_launch_dependents();
     __syncthreads();
@@ -60,7 +62,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(uint32_t*
         }
         uint32_t tsum = 0;
 #pragma unroll
-        for (int j = 0; j < SCAN_ITEMS; ++j) tsum += v[j];
+        for (int j = 0; j < SCAN_ITEMS; ++j) { tsum += v[j]; my64 += v[j]; }
         uint32_t incl = tsum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -101,12 +103,19 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(uint32_t*
         if (tid == SCAN_THREADS - 1) s_carry = run;
         __syncthreads();
     }
+    if (total_host) {  // uniform
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) my64 += __shfl_xor_sync(0xffffffffu, my64, d);
+        if (lane == 0 && my64) atomicAdd(&s_total64, my64);
+        __syncthreads();
+    }
     if (tid == 0) {
         const uint32_t total = s_carry;
         *total_dev = total;
         if (total_host) {
-            if (sums2) total_host[1] = s_total2;
-            total_host[0] = total;
+            if (sums2) total_host[SLOT_RC] = s_total2;
+            // a sum beyond the sort's 30-bit counters is published as 0xffffffff (GSR_ERR_TOO_MANY_PAIRS on the host)
+            total_host[SLOT_R] = s_total64 >= (1ull << 30) ? 0xffffffffu : total;
             __threadfence_system();
         }
     }
@@ -219,7 +228,7 @@ __global__ void __launch_bounds__(PRE_THREADS) duplicate_sorted_kernel(
     const int P_all, const int grid_x, const uint32_t* __restrict__ sorted_ids, const uint2* __restrict__ sorted_rects,
     const uint32_t* __restrict__ block_offsets, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
     uint32_t* __restrict__ hist, const int tile_bits, const uint32_t* __restrict__ n_sorted, const int coarse,
-    unsigned long long* __restrict__ fuse_state, const int fuse_blocks) {
+    unsigned long long* __restrict__ fuse_state, const int fuse_blocks, uint32_t* error_flag) {
     __shared__ uint32_t s_excl[DUP_GAUSS + 1];
     // 16-byte aligned: the compiler reads the 8 warp sums with LDS.128, which otherwise straddles s_excl[DUP_GAUSS]
     // (unused lane of the vector, but compute-sanitizer racecheck rightly flags the overlap with its later store)
@@ -319,7 +328,16 @@ __global__ void __launch_bounds__(PRE_THREADS) duplicate_sorted_kernel(
                 const int j = look - lane;
                 unsigned long long v = FUSE_INC;  // lanes before block 0: an inclusive prefix of zero
                 if (j >= 0) {
-                    do { v = st[j]; } while ((v & 3ull) == 0ull);
+                    // blocks are ticketed, so block j has started; bounded like the sort's look-back (radix_sort.cu)
+                    uint32_t spins = 0;
+                    while (((v = st[j]) & 3ull) == 0ull) {
+                        if (++spins > (1u << 22)) {
+                            gsr_raise_error(error_flag);
+                            v = FUSE_INC;  // give up: the frame is invalid, the call reports GSR_ERR_SORT_STALLED
+                            break;
+                        }
+                        __nanosleep(32);
+                    }
                 }
                 const unsigned inc = __ballot_sync(0xffffffffu, (v & 3ull) == FUSE_INC);
                 const int first = inc ? (__ffs((int)inc) - 1) : 32;  // nearest block holding an inclusive prefix
@@ -495,7 +513,7 @@ int launch_duplicate_sorted(int P, int grid_x, const uint32_t* sorted_ids, const
     GSR_CARVEOUT(duplicate_sorted_kernel<false>, "DUP", -1);
     duplicate_sorted_kernel<false><<<blocks, PRE_THREADS, 0, s>>>(
         P, grid_x, sorted_ids, reinterpret_cast<const uint2*>(sorted_rects), block_offsets, keys32_out, vals_out, hist,
-        tile_bits, n_sorted, 0, nullptr, 0);
+        tile_bits, n_sorted, 0, nullptr, 0, nullptr);
     cudaError_t e = cudaPeekAtLastError();
     return e == cudaSuccess ? 1 : -(int)e;
 }
@@ -504,14 +522,14 @@ size_t duplicate_fused_state_bytes(int P) { return ((size_t)num_dup_blocks(P) + 
 
 int launch_duplicate_fused(int P, int grid_x, const uint32_t* sorted_ids, const uint32_t* tile_rects, bool coarse,
                            void* fuse_state, uint32_t* keys32_out, uint32_t* vals_out, uint32_t* hist, int tile_bits,
-                           cudaStream_t s, const uint32_t* n_sorted) {
+                           cudaStream_t s, const uint32_t* n_sorted, uint32_t* error_flag) {
     if (P <= 0) return 0;
     if (tile_bits < 1 || tile_bits > 32 || !fuse_state) return GSR_ERR_INVALID_ARG;
     const int blocks = num_dup_blocks(P);
     GSR_CARVEOUT(duplicate_sorted_kernel<true>, "DUP", -1);
     duplicate_sorted_kernel<true><<<blocks, PRE_THREADS, 0, s>>>(
         P, grid_x, sorted_ids, reinterpret_cast<const uint2*>(tile_rects), nullptr, keys32_out, vals_out, hist, tile_bits,
-        n_sorted, coarse ? 1 : 0, static_cast<unsigned long long*>(fuse_state), blocks);
+        n_sorted, coarse ? 1 : 0, static_cast<unsigned long long*>(fuse_state), blocks, error_flag);
     cudaError_t e = cudaPeekAtLastError();
     return e == cudaSuccess ? 1 : -(int)e;
 }

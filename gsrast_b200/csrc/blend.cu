@@ -184,11 +184,9 @@ static_assert(CBATCH <= BLEND_THREADS && CBATCH % 32 == 0, "one staging thread p
 #ifndef GSR_BLEND_MINB
 #define GSR_BLEND_MINB 6   // 40 registers (12 B of spills outside the candidate loop): 48 resident warps, blend -2.6 %
 #endif
-#ifdef GSR_BLEND_STATS
-// diagnostics build only (tools/blend_stats.py): [0] tile-rounds staged, [1] warp-rounds that walked a list,
-// [2] candidates listed (warp level), [3] tile-rounds the deepest n_contrib of the tile needed
-__device__ unsigned long long g_blend_stats[4];
-#endif
+// COUNT: the same kernel with work counters (gsr_stage_times.blend_counters, GSR_FLAG_BLEND_COUNT) — a separate
+// instantiation for reporting; the default one carries none of it.
+template <bool COUNT>
 __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_kernel(const BlendParams p) {
     __shared__ float4 s_splat[CBATCH * 3];
     __shared__ unsigned char s_mask[CBATCH];                     // bit w: splat can reach warp w's 8x4 sub-rectangle
@@ -247,9 +245,10 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
 
     for (int r = 0; r < rounds; ++r) {
         if (__syncthreads_and(warp_done)) break;
-#ifdef GSR_BLEND_STATS
-        if (tid == 0) atomicAdd(&g_blend_stats[0], 1ull);
-#endif
+        if (COUNT && tid == 0) {
+            atomicAdd(p.counters + 0, 1ull);
+            atomicAdd(p.counters + 7, (unsigned long long)min(CBATCH, total - r * CBATCH));
+        }
         const int progress = r * CBATCH + tid;
         uint32_t m = 0;
         const float2 xy = n_xy;
@@ -318,9 +317,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
                 n += __popc(bits);
             }
             __syncwarp();
-#ifdef GSR_BLEND_STATS
-            if (lane == 0) { atomicAdd(&g_blend_stats[1], 1ull); atomicAdd(&g_blend_stats[2], (unsigned long long)n); }
-#endif
+            if (COUNT && lane == 0) { atomicAdd(p.counters + 1, 1ull); atomicAdd(p.counters + 2, (unsigned long long)n); }
+            uint32_t c_trips = 0, c_live = 0, c_cand = 0, c_blend = 0;
             // Branch-free inner loop.  A terminated pixel carries its final transmittance as a NEGATIVE T:
             // then w = alpha*T and T - w are negative, "T - w >= t_min" fails, nothing is blended, and
             // no separate `done` flag has to be tested.  Per candidate: LDS.U16, 2 LDS.128, 8 FP32 for the
@@ -348,6 +346,12 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
                     const bool cand = (p2 <= 0.0f) && (alpha >= ALPHA_MIN);
                     const bool pass = test_T >= t_min;
                     const bool ok = cand && pass;
+                    if (COUNT) {
+                        ++c_trips;
+                        c_live += T > 0.0f;
+                        c_cand += cand && T > 0.0f;
+                        c_blend += ok;
+                    }
                     if (ok) {
                         C0 = fmaf(b.z, w, C0);
                         C1 = fmaf(b.w, w, C1);
@@ -364,19 +368,19 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
                 }
             }
             if (last_off != 0xffffffffu) last = (uint32_t)(r * CBATCH + 1) + (last_off - rec_bias) / 48u;
+            if (COUNT) {
+                c_live = __reduce_add_sync(0xffffffffu, c_live);
+                c_cand = __reduce_add_sync(0xffffffffu, c_cand);
+                c_blend = __reduce_add_sync(0xffffffffu, c_blend);
+                if (lane == 0) {
+                    atomicAdd(p.counters + 3, (unsigned long long)c_trips);
+                    atomicAdd(p.counters + 4, (unsigned long long)c_live);
+                    atomicAdd(p.counters + 5, (unsigned long long)c_cand);
+                    atomicAdd(p.counters + 6, (unsigned long long)c_blend);
+                }
+            }
         }
     }
-#ifdef GSR_BLEND_STATS
-    {
-        __shared__ unsigned s_maxlast;
-        __syncthreads();
-        if (tid == 0) s_maxlast = 0;
-        __syncthreads();
-        atomicMax(&s_maxlast, last);
-        __syncthreads();
-        if (tid == 0) atomicAdd(&g_blend_stats[3], (unsigned long long)((s_maxlast + CBATCH - 1) / CBATCH));
-    }
-#endif
     T = fabsf(T);
     if (inside) {
         const size_t pix = (size_t)pix_y * p.W + pix_x;
@@ -402,27 +406,18 @@ __global__ void fill_background_kernel(int n, const float* __restrict__ backgrou
 
 }  // namespace
 
-#ifdef GSR_BLEND_STATS
-extern "C" int gsr_debug_blend_stats(unsigned long long* out, int reset) {
-    cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out, g_blend_stats, sizeof(g_blend_stats));
-    if (reset) {
-        unsigned long long z[4] = {0, 0, 0, 0};
-        cudaMemcpyToSymbol(g_blend_stats, z, sizeof(z));
-    }
-    return 0;
-}
-#endif
-
 int launch_blend(const BlendParams& p, bool simple, cudaStream_t s) {
     const int tiles = p.grid_x * p.grid_y;
     if (tiles <= 0) return 0;
     cudaError_t e;
     if (simple)
         e = launch_pdl(blend_simple_kernel, dim3(tiles), dim3(BLEND_THREADS), 0, s, p);
-    else {
-        GSR_CARVEOUT(blend_culled_kernel, "BLEND", GSR_BLEND_CARVEOUT);
-        e = launch_pdl(blend_culled_kernel, dim3(tiles), dim3(BLEND_THREADS), 0, s, p);
+    else if (p.counters) {
+        GSR_CARVEOUT(blend_culled_kernel<true>, "BLEND", GSR_BLEND_CARVEOUT);
+        e = launch_pdl(blend_culled_kernel<true>, dim3(tiles), dim3(BLEND_THREADS), 0, s, p);
+    } else {
+        GSR_CARVEOUT(blend_culled_kernel<false>, "BLEND", GSR_BLEND_CARVEOUT);
+        e = launch_pdl(blend_culled_kernel<false>, dim3(tiles), dim3(BLEND_THREADS), 0, s, p);
     }
     return e == cudaSuccess ? 1 : -(int)e;
 }

@@ -38,8 +38,12 @@ void obtain(char*& chunk, T*& out, size_t bytes, size_t align = 128) {
 
 int num_pre_blocks(int P) { return (P + PRE_THREADS - 1) / PRE_THREADS; }
 
-// Mapped pinned slot for the num_rendered readback, one per host thread and device.
-thread_local HostSlot g_slot;
+// Mapped pinned slot for the num_rendered readback, one per host thread and device; released when the thread ends
+// (at process exit the runtime may already be gone: the calls then fail harmlessly).
+struct ThreadSlot : HostSlot {
+    ~ThreadSlot() { release_slot(*this); }
+};
+thread_local ThreadSlot g_slot;
 
 }  // namespace
 
@@ -51,6 +55,7 @@ int ensure_slot(HostSlot& s) {
     s.host = nullptr;
     void* h = nullptr;
     GSR_CUDA_TRY(cudaHostAlloc(&h, 64, cudaHostAllocMapped));
+    memset(h, 0, 64);
     s.host = static_cast<uint32_t*>(h);
     void* d = nullptr;
     GSR_CUDA_TRY(cudaHostGetDevicePointer(&d, h, 0));
@@ -70,18 +75,32 @@ void release_slot(HostSlot& s) {
     s.device = -1;
 }
 
+// The sort's look-back watchdog reports into word SLOT_ERROR of the slot (sticky, like a CUDA asynchronous error): the
+// host looks at it wherever it already holds the slot in its hands — on entry of the next call, behind the
+// num_rendered wait, and after every stream synchronisation the library does itself.
+int take_async_error(HostSlot& s) {
+    if (!s.host) return 0;
+    volatile uint32_t* w = s.host;
+    if (w[SLOT_ERROR] == 0u) return 0;
+    w[SLOT_ERROR] = 0u;
+    return GSR_ERR_SORT_STALLED;
+}
+
 namespace {
 
+// Stage events of one call (only when the caller asked for timings); destroyed on every way out of forward_impl.
 struct StageTimer {
     bool on = false;
     cudaStream_t s = nullptr;
-    cudaEvent_t ev[10];
+    cudaEvent_t ev[10] = {};
+    cudaEvent_t sort_ev[16] = {};  // [0..11] the two sort halves, [12..15] count / fill kernels of the bin expansion
     int n = 0;
     int init(bool enable, cudaStream_t stream) {
-        on = enable;
         s = stream;
-        if (!on) return 0;
+        if (!enable) return 0;
+        on = true;
         for (auto& e : ev) GSR_CUDA_TRY(cudaEventCreate(&e));
+        for (auto& e : sort_ev) GSR_CUDA_TRY(cudaEventCreate(&e));
         return 0;
     }
     void mark() {
@@ -92,10 +111,17 @@ struct StageTimer {
         if (on && a < n && b < n) cudaEventElapsedTime(&t, ev[a], ev[b]);
         return t;
     }
-    void destroy() {
-        if (on)
-            for (auto& e : ev) cudaEventDestroy(e);
-        on = false;
+    float sort_ms(int a, int b) {
+        float t = 0.f;
+        if (on) cudaEventElapsedTime(&t, sort_ev[a], sort_ev[b]);
+        return t;
+    }
+    ~StageTimer() {
+        if (!on) return;
+        for (auto& e : ev)
+            if (e) cudaEventDestroy(e);
+        for (auto& e : sort_ev)
+            if (e) cudaEventDestroy(e);
     }
 };
 
@@ -157,6 +183,7 @@ size_t gsr_image_state_map(char* chunk, int width, int height, gsr_image_state* 
     obtain(c, st.n_contrib, N * sizeof(uint32_t));
     obtain(c, st.accum_alpha, N * sizeof(float));
     obtain(c, st.tile_order, T * sizeof(uint32_t));
+    obtain(c, st.blend_counters, GSR_BLEND_COUNTERS * sizeof(unsigned long long));
     if (im) *im = st;
     return (size_t)(c - chunk);
 }
@@ -188,6 +215,13 @@ int gsr_forward_ex(const gsr_forward_args* a) { return gsr::forward_impl(a, null
 #ifndef GSR_FUSED_DUP
 #define GSR_FUSED_DUP 0
 #endif
+// every stage launcher returns the number of kernels it launched, or a negative error
+#define GSR_STAGE(call)       \
+    do {                      \
+        rc = (call);          \
+        if (rc < 0) return rc;\
+        launches += rc;       \
+    } while (0)
 int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
     HostSlot& slot = slot_in ? *slot_in : g_slot;
     if (!a || !a->geometry_alloc || !a->binning_alloc || !a->image_alloc) return GSR_ERR_INVALID_ARG;
@@ -204,31 +238,26 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
     cudaStream_t s = static_cast<cudaStream_t>(a->stream);
     const int P = a->P, W = a->width, H = a->height;
     const int gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
+    // tile rects are packed 16 + 16 bits, and 256 Gaussians x (tiles per Gaussian <= gx*gy) must fit the 32-bit block
+    // sums of the scan (GSCuda.cu:771 scans in 32 bits as well); 2^23 tiles = a 46 000 x 46 000 pixel image
+    if (gx > 0xffff || gy > 0xffff || (long long)gx * gy > (1ll << 23)) return GSR_ERR_INVALID_ARG;
     const int tiles = gx * gy;
     int launches = 0, rc = 0;
 
     StageTimer tm;
     if ((rc = tm.init(a->timings != nullptr, s)) < 0) return rc;
-#define GSR_STAGE(call)               \
-    do {                              \
-        rc = (call);                  \
-        if (rc < 0) {                 \
-            tm.destroy();             \
-            return rc;                \
-        }                             \
-        launches += rc;               \
-    } while (0)
+    cudaEvent_t* sort_ev = tm.on ? tm.sort_ev : nullptr;
 
     // geometry chunk (GSCuda.cu:723-729)
     char* gchunk = a->geometry_alloc(gsr_geometry_state_required(P), a->geometry_user);
-    if (!gchunk) { tm.destroy(); return GSR_ERR_ALLOC_FAILED; }
+    if (!gchunk) return GSR_ERR_ALLOC_FAILED;
     gsr_geometry_state geom;
     gsr_geometry_state_map(gchunk, P, &geom);
     int* radii = a->radii ? a->radii : geom.internal_radii;
 
     // image chunk (GSCuda.cu:734-736)
     char* ichunk = a->image_alloc(gsr_image_state_required(W, H), a->image_user);
-    if (!ichunk) { tm.destroy(); return GSR_ERR_ALLOC_FAILED; }
+    if (!ichunk) return GSR_ERR_ALLOC_FAILED;
     gsr_image_state img;
     gsr_image_state_map(ichunk, W, H, &img);
 
@@ -240,31 +269,16 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
     const int bin_bits = (int)gsr_get_higher_msb((uint32_t)nbins);
     const int tile_passes = sort_num_passes(bin_mode ? bin_bits : tile_bits);
     const int depth_passes = sort_num_passes(32);
-    cudaEvent_t sort_ev[16];  // [0..11] the two sort halves, [12..15] count / fill kernels of the bin expansion
-    const bool sort_timed = tm.on;
-    if (sort_timed)
-        for (auto& e : sort_ev) cudaEventCreate(&e);
-#define GSR_FAIL(code)                                     \
-    do {                                                   \
-        if (sort_timed)                                    \
-            for (auto& e : sort_ev) cudaEventDestroy(e);   \
-        tm.destroy();                                      \
-        return (code);                                     \
-    } while (0)
-#undef GSR_STAGE
-#define GSR_STAGE(call)          \
-    do {                         \
-        rc = (call);             \
-        if (rc < 0) GSR_FAIL(rc);\
-        launches += rc;          \
-    } while (0)
 
     uint32_t R = 0, Rc = 0;
     bool fused_dup = false;
     const uint32_t* n_depth = nullptr;  // device: Gaussians the depth sort kept
+    uint32_t* sort_error = nullptr;     // device address of the slot's sticky error word
     tm.mark();  // 0
     if (P > 0) {
-        if ((rc = ensure_slot(slot)) < 0) GSR_FAIL(rc);
+        if ((rc = ensure_slot(slot)) < 0) return rc;
+        if ((rc = take_async_error(slot)) < 0) return rc;  // a watchdog of an earlier call on this slot tripped
+        sort_error = slot.dev + SLOT_ERROR;
         PreprocessParams pp;
         memset(&pp, 0, sizeof(pp));
         pp.P = P; pp.D = a->D; pp.M = a->M; pp.W = W; pp.H = H; pp.grid_x = gx; pp.grid_y = gy;
@@ -293,23 +307,16 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         // lean callers need no point_offsets, so the duplication can gather its rects and find its offsets itself
         // (binning.cu, duplicate_sorted_kernel<true>) instead of running behind gather_rects + a single-CTA scan
         fused_dup = lean && GSR_FUSED_DUP != 0;
-        if (fused_dup) {
-            cudaError_t ez = cudaMemsetAsync(geom.sorted_block_sums, 0, duplicate_fused_state_bytes(P), s);
-            if (ez != cudaSuccess) GSR_FAIL(-(int)ez);
-        }
+        if (fused_dup) GSR_CUDA_TRY(cudaMemsetAsync(geom.sorted_block_sums, 0, duplicate_fused_state_bytes(P), s));
         // all clears of the frame up front, so the kernels behind them form uninterrupted dependent-launch chains
-        if (!sort32_prepare(geom.depth_sort_space, (size_t)P, 32, s)) GSR_FAIL(-(int)cudaGetLastError());
-        {
-            cudaError_t ez = cudaMemsetAsync(img.ranges, 0, sizeof(uint32_t) * 2 * (size_t)tiles, s);
-            if (ez != cudaSuccess) GSR_FAIL(-(int)ez);
-        }
+        if (!sort32_prepare(geom.depth_sort_space, (size_t)P, 32, s)) return -(int)cudaGetLastError();
+        GSR_CUDA_TRY(cudaMemsetAsync(img.ranges, 0, sizeof(uint32_t) * 2 * (size_t)tiles, s));
         GSR_STAGE(launch_preprocess(pp, compat, s));
         tm.mark();  // 1
         const int nb = num_pre_blocks(P);
         GSR_STAGE(launch_scan_block_sums(geom.block_sums, nb, geom.block_sums + nb, slot.dev, s,
                                          bin_mode ? geom.coarse_block_sums : nullptr));
-        cudaError_t e = cudaEventRecord(slot.landed, s);
-        if (e != cudaSuccess) GSR_FAIL(-(int)e);
+        GSR_CUDA_TRY(cudaEventRecord(slot.landed, s));
         tm.mark();  // 2
         // ---- depth half of the sort: P records, queued before the host waits --------------------
         Sort32Plan dp;
@@ -320,11 +327,12 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         dp.vbuf[0] = geom.depth_sort_ids[0]; dp.vbuf[1] = geom.depth_sort_ids[1];
         dp.keys_out = geom.depth_sort_keys[1]; dp.vals_out = geom.depth_sort_ids[1];
         dp.temp = geom.depth_sort_space; dp.hist_ready = false;
+        dp.error_flag = sort_error;
         // Gaussians that emit nothing carry the key 0xffffffff (preprocess): the sort drops them, so its later
         // passes, the rect gather and the duplication only see the n_depth <= P Gaussians that are on screen
         dp.drop_pad = true;
         n_depth = sort32_kept_count(geom.depth_sort_space, (size_t)P, 32);
-        GSR_STAGE(launch_sort32(dp, s, sort_timed ? sort_ev : nullptr));
+        GSR_STAGE(launch_sort32(dp, s, sort_ev));
         // tile rects into depth order + scan of the per-block pair counts (same total, other order)
         if (!fused_dup) GSR_STAGE(launch_gather_rects(P, geom.depth_sort_ids[1], geom.tile_rects, geom.sorted_rects,
                                       geom.sorted_block_sums, geom.tiles_touched, geom.block_sums,
@@ -333,10 +341,10 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         if (!fused_dup) GSR_STAGE(launch_scan_block_sums(geom.sorted_block_sums, ndb, geom.sorted_block_sums + ndb, nullptr, s));
         tm.mark();  // 3
         // the one host round trip: num_rendered decides the binning allocation (GSCuda.cu:772,782)
-        e = cudaEventSynchronize(slot.landed);
-        if (e != cudaSuccess) GSR_FAIL(-(int)e);
-        R = static_cast<volatile uint32_t*>(slot.host)[0];
-        Rc = bin_mode ? static_cast<volatile uint32_t*>(slot.host)[1] : 0u;
+        GSR_CUDA_TRY(cudaEventSynchronize(slot.landed));
+        R = static_cast<volatile uint32_t*>(slot.host)[SLOT_R];
+        Rc = bin_mode ? static_cast<volatile uint32_t*>(slot.host)[SLOT_RC] : 0u;
+        if ((rc = take_async_error(slot)) < 0) return rc;
     } else {
         tm.mark();
         tm.mark();
@@ -347,21 +355,24 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         // GSCuda.cu:775-778 returns here leaving out_color stale; the contract renders background.
         if (!compat) GSR_STAGE(launch_fill_background(W, H, a->background, a->out_color, img.accum_alpha, img.n_contrib, s));
         if (a->timings) {
-            cudaStreamSynchronize(s);
+            GSR_CUDA_TRY(cudaStreamSynchronize(s));
             memset(a->timings, 0, sizeof(*a->timings));
             a->timings->preprocess_ms = tm.ms(0, 1);
             a->timings->scan_ms = tm.ms(1, 2);
             a->timings->depth_sort_ms = tm.ms(2, 3);
             a->timings->total_ms = tm.ms(0, 3);
             a->timings->kernel_launches = launches;
+            if (P > 0 && (rc = take_async_error(slot)) < 0) return rc;
         }
-        GSR_FAIL(0);
+        return 0;
     }
-    if (R >= (1u << 30)) GSR_FAIL(GSR_ERR_TOO_MANY_PAIRS);
+    // the scan kernel adds the per-block counts up in 64 bits and publishes 0xffffffff when the sum does not fit the
+    // sort's 30-bit counters (the 32-bit sum the reference would use, GSCuda.cu:771, may have wrapped to anything)
+    if (R >= (1u << 30)) return GSR_ERR_TOO_MANY_PAIRS;
 
     // binning chunk (GSCuda.cu:782-784)
     char* bchunk = a->binning_alloc(gsr_binning_state_required(R), a->binning_user);
-    if (!bchunk) GSR_FAIL(GSR_ERR_ALLOC_FAILED);
+    if (!bchunk) return GSR_ERR_ALLOC_FAILED;
     gsr_binning_state bin;
     gsr_binning_state_map(bchunk, R, &bin);
 
@@ -373,12 +384,13 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
     if (bin_mode) {
         // (Gaussian, bin) records in depth order -> stable sort by bin id -> expansion of every bin into the
         // sorted per-tile lists and the tile ranges (bin_expand.cu)
-        if (Rc == 0 || Rc > R) GSR_FAIL(GSR_ERR_INVALID_ARG);  // cannot happen: every pair lies in one of its Gaussian's bins
+        if (Rc == 0 || Rc > R) return GSR_ERR_INVALID_ARG;  // cannot happen: every pair lies in one of its Gaussian's bins
         uint32_t* bin_hist = sort32_prepare(tile_temp, (size_t)Rc, bin_bits, s);
-        if (!bin_hist) GSR_FAIL(-(int)cudaGetLastError());
+        if (!bin_hist) return -(int)cudaGetLastError();
         if (fused_dup)
             GSR_STAGE(launch_duplicate_fused(P, bins_x, geom.depth_sort_ids[1], geom.tile_rects, /*coarse=*/true,
-                                             geom.sorted_block_sums, k32[0], v32[0], bin_hist, bin_bits, s, n_depth));
+                                             geom.sorted_block_sums, k32[0], v32[0], bin_hist, bin_bits, s, n_depth,
+                                             sort_error));
         else
             GSR_STAGE(launch_duplicate_sorted(P, bins_x, geom.depth_sort_ids[1], geom.sorted_rects, geom.sorted_block_sums,
                                               k32[0], v32[0], bin_hist, bin_bits, s, n_depth));
@@ -393,7 +405,8 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
             tp.vbuf[0] = v32[1]; tp.vbuf[1] = v32[0];
             tp.keys_out = k32[out]; tp.vals_out = v32[out];
             tp.temp = tile_temp; tp.hist_ready = true;
-            GSR_STAGE(launch_sort32(tp, s, sort_timed ? sort_ev + 6 : nullptr));
+            tp.error_flag = sort_error;
+            GSR_STAGE(launch_sort32(tp, s, sort_ev ? sort_ev + 6 : nullptr));
         }
         tm.mark();  // 5
         ExpandPlan ep;
@@ -407,14 +420,15 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         ep.tile_counts = img.tile_order; ep.ranges = img.ranges;
         ep.keys_out = bin.point_list_keys; ep.vals_out = bin.point_list;
         ep.r1_quirk = compat && R == 1;
-        GSR_STAGE(launch_bin_expand(ep, s, sort_timed ? sort_ev + 12 : nullptr));
+        GSR_STAGE(launch_bin_expand(ep, s, sort_ev ? sort_ev + 12 : nullptr));
         tm.mark();  // 6
     } else {
         uint32_t* tile_hist = sort32_prepare(tile_temp, (size_t)R, tile_bits, s);
-        if (!tile_hist) GSR_FAIL(-(int)cudaGetLastError());
+        if (!tile_hist) return -(int)cudaGetLastError();
         if (fused_dup)
             GSR_STAGE(launch_duplicate_fused(P, gx, geom.depth_sort_ids[1], geom.tile_rects, /*coarse=*/false,
-                                             geom.sorted_block_sums, k32[0], v32[0], tile_hist, tile_bits, s, n_depth));
+                                             geom.sorted_block_sums, k32[0], v32[0], tile_hist, tile_bits, s, n_depth,
+                                             sort_error));
         else
             GSR_STAGE(launch_duplicate_sorted(P, gx, geom.depth_sort_ids[1], geom.sorted_rects, geom.sorted_block_sums, k32[0],
                                               v32[0], tile_hist, tile_bits, s, n_depth));
@@ -430,7 +444,8 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
             tp.expand_low = reinterpret_cast<const uint32_t*>(geom.depths);  // key = tile << 32 | depth bits
             tp.keys_out64 = bin.point_list_keys;
             tp.temp = tile_temp; tp.hist_ready = true;
-            GSR_STAGE(launch_sort32(tp, s, sort_timed ? sort_ev + 6 : nullptr));
+            tp.error_flag = sort_error;
+            GSR_STAGE(launch_sort32(tp, s, sort_ev ? sort_ev + 6 : nullptr));
         }
         tm.mark();  // 5
         GSR_STAGE(launch_identify_ranges(bin.point_list_keys, R, img.ranges, tiles, compat, s, /*zero_first=*/false));
@@ -446,13 +461,17 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
     bp.final_T = img.accum_alpha; bp.n_contrib = img.n_contrib; bp.out_color = a->out_color;
     bp.t_min = compat ? 0.001f : 0.0001f;  // GSCuda.cu:653 vs contract
     bp.tile_order = nullptr;
+    // GSR_FLAG_BLEND_COUNT: the counting instantiation of the blend (same arithmetic + work counters), for reporting
+    const bool count = (a->flags & GSR_FLAG_BLEND_COUNT) != 0 && a->timings != nullptr;
+    if (count) {
+        GSR_CUDA_TRY(cudaMemsetAsync(img.blend_counters, 0, GSR_BLEND_COUNTERS * sizeof(unsigned long long), s));
+        bp.counters = img.blend_counters;
+    }
     GSR_STAGE(launch_blend(bp, (a->flags & GSR_FLAG_BLEND_SIMPLE) != 0, s));
     tm.mark();  // 7
-#undef GSR_STAGE
 
     if (a->timings) {
-        cudaError_t e = cudaStreamSynchronize(s);
-        if (e != cudaSuccess) GSR_FAIL(-(int)e);
+        GSR_CUDA_TRY(cudaStreamSynchronize(s));
         gsr_stage_times* t = a->timings;
         memset(t, 0, sizeof(*t));
         t->preprocess_ms = tm.ms(0, 1);
@@ -463,8 +482,8 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         t->ranges_ms = bin_mode ? 0.f : tm.ms(5, 6);
         t->expand_ms = bin_mode ? tm.ms(5, 6) : 0.f;
         if (bin_mode && Rc) {
-            cudaEventElapsedTime(&t->expand_count_ms, sort_ev[12], sort_ev[13]);
-            cudaEventElapsedTime(&t->expand_fill_ms, sort_ev[14], sort_ev[15]);
+            t->expand_count_ms = tm.sort_ms(12, 13);
+            t->expand_fill_ms = tm.sort_ms(14, 15);
         }
         t->num_coarse = (int)Rc;
         t->binning_mode = bin_mode ? 0 : 1;
@@ -474,21 +493,18 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         t->depth_passes = depth_passes;
         t->sort_passes = depth_passes + tile_passes;
         t->kernel_launches = launches;
-        float h0 = 0.f, h1 = 0.f;
-        cudaEventElapsedTime(&h0, sort_ev[0], sort_ev[1]);
-        cudaEventElapsedTime(&h1, sort_ev[6], sort_ev[7]);
-        t->sort_hist_ms = h0 + h1;
-        for (int i = 0; i < depth_passes && i < 4; ++i) cudaEventElapsedTime(&t->sort_pass_ms[i], sort_ev[1 + i], sort_ev[2 + i]);
+        t->sort_hist_ms = tm.sort_ms(0, 1) + tm.sort_ms(6, 7);
+        for (int i = 0; i < depth_passes && i < 4; ++i) t->sort_pass_ms[i] = tm.sort_ms(1 + i, 2 + i);
         for (int i = 0; i < tile_passes && depth_passes + i < 8; ++i)
-            cudaEventElapsedTime(&t->sort_pass_ms[depth_passes + i], sort_ev[7 + i], sort_ev[8 + i]);
+            t->sort_pass_ms[depth_passes + i] = tm.sort_ms(7 + i, 8 + i);
+        if (count)
+            GSR_CUDA_TRY(cudaMemcpy(t->blend_counters, img.blend_counters, GSR_BLEND_COUNTERS * sizeof(unsigned long long),
+                                    cudaMemcpyDeviceToHost));
+        if ((rc = take_async_error(slot)) < 0) return rc;  // the stream is idle: this call's own passes have reported
     }
-    if (sort_timed)
-        for (auto& e : sort_ev) cudaEventDestroy(e);
-    tm.destroy();
-#undef GSR_STAGE
-#undef GSR_FAIL
     return (int)R;
 }
+#undef GSR_STAGE
 
 extern "C" {
 
@@ -548,7 +564,12 @@ int gsr_sort_pairs(uint64_t* keys_in, uint32_t* vals_in, uint64_t* keys_out, uin
                    char* temp, void* stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     bool in_a = false;
-    int rc = launch_sort_pairs(keys_in, vals_in, keys_out, vals_out, n, end_bit, temp, &in_a, s);
+    // the watchdog reports into the calling thread's slot: asynchronous, surfaced by this thread's next call
+    int rc = ensure_slot(g_slot);
+    if (rc < 0) return rc;
+    if ((rc = take_async_error(g_slot)) < 0) return rc;
+    rc = launch_sort_pairs(keys_in, vals_in, keys_out, vals_out, n, end_bit, temp, &in_a, s, nullptr,
+                           g_slot.dev + SLOT_ERROR);
     if (rc < 0) return rc;
     if (in_a && n > 0) {
         GSR_CUDA_TRY(cudaMemcpyAsync(keys_out, keys_in, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
@@ -568,7 +589,7 @@ const char* gsr_error_string(int code) {
     switch (code) {
         case GSR_ERR_INVALID_ARG: return "gsrast_b200: invalid argument";
         case GSR_ERR_ALLOC_FAILED: return "gsrast_b200: scratch allocator returned NULL";
-        case GSR_ERR_TOO_MANY_PAIRS: return "gsrast_b200: num_rendered >= 2^30";
+        case GSR_ERR_TOO_MANY_PAIRS: return "gsrast_b200: num_rendered >= 2^30 (or the image has more than 2^23 tiles)";
         case GSR_ERR_SORT_STALLED: return "gsrast_b200: radix sort look-back watchdog tripped";
         case GSR_ERR_PLY_OPEN: return "gsrast_b200: cannot open the .ply file";
         case GSR_ERR_PLY_FORMAT: return "gsrast_b200: .ply header has no vertex count on line 3 or no end_header";

@@ -93,7 +93,7 @@ int launch_duplicate_sorted(int P, int grid_x, const uint32_t* sorted_ids, const
 size_t duplicate_fused_state_bytes(int P);
 int launch_duplicate_fused(int P, int grid_x, const uint32_t* sorted_ids, const uint32_t* tile_rects, bool coarse,
                            void* fuse_state, uint32_t* keys32_out, uint32_t* vals_out, uint32_t* hist, int tile_bits,
-                           cudaStream_t s, const uint32_t* n_sorted = nullptr);
+                           cudaStream_t s, const uint32_t* n_sorted = nullptr, uint32_t* error_flag = nullptr);
 // zero_first: clear ranges[num_tiles] here (otherwise the caller has already done it)
 int launch_identify_ranges(const uint64_t* keys, size_t n, uint32_t* ranges, int num_tiles, bool compat,
                            cudaStream_t s, bool zero_first = true);
@@ -106,7 +106,8 @@ int sort_num_passes(int end_bit);
 // that the sorted lists land in point_list_keys / point_list without a final copy.
 // `events` (optional, passes+2 entries) are recorded before the histogram, after it, and after every pass.
 int launch_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, size_t n, int end_bit,
-                      char* temp, bool* result_in_a, cudaStream_t s, cudaEvent_t* events = nullptr);
+                      char* temp, bool* result_in_a, cudaStream_t s, cudaEvent_t* events = nullptr,
+                      uint32_t* error_flag = nullptr);
 
 // 32-bit-key LSD sort over bits [0,end_bit) (<= 4 passes).  Pass p reads the input (p == 0) or
 // buffer (p-1)&1 and writes buffer p&1, the last pass writes the outputs (which may alias a buffer the
@@ -129,6 +130,8 @@ struct Sort32Plan {
     // the later passes and every consumer work on the first sort32_kept_count() entries of the output only
     // (the rest of the output arrays is undefined).  Needs >= 2 passes and !hist_ready.
     bool drop_pad;
+    // device word the look-back watchdog sets when it trips (nullptr: a word inside `temp`, which nobody reads back)
+    uint32_t* error_flag;
 };
 // Device word that holds the number of kept keys after launch_sort32 with drop_pad (same temp, n, end_bit).
 const uint32_t* sort32_kept_count(char* temp, size_t n, int end_bit);
@@ -186,12 +189,16 @@ struct BlendParams {
     float* out_color;
     float t_min;                 // 0.0001f contract, 0.001f GSRast
     const uint32_t* tile_order;  // optional
+    unsigned long long* counters;  // optional [GSR_BLEND_COUNTERS]: run the counting instantiation (GSR_FLAG_BLEND_COUNT)
 };
 int launch_blend(const BlendParams& p, bool simple, cudaStream_t s);
 int launch_fill_background(int W, int H, const float* background, float* out_color, float* final_T,
                            uint32_t* n_contrib, cudaStream_t s);
 
-// Mapped pinned word that receives num_rendered (the pipeline's only host round trip).
+// Mapped pinned words (64 bytes) the device reports into; SLOT_R is the pipeline's only host round trip.
+constexpr int SLOT_R = 0;      // num_rendered; 0xffffffff = the pair count does not fit (scan_block_sums_kernel)
+constexpr int SLOT_RC = 1;     // (Gaussian, bin) records of the bin-expansion path
+constexpr int SLOT_ERROR = 4;  // sticky: set by the look-back watchdogs (radix_sort.cu, binning.cu), taken by the host
 struct HostSlot {
     uint32_t* host = nullptr;
     uint32_t* dev = nullptr;
@@ -200,6 +207,8 @@ struct HostSlot {
 };
 int ensure_slot(HostSlot& s);
 void release_slot(HostSlot& s);
+// GSR_ERR_SORT_STALLED (and the word cleared) when a watchdog reported into the slot since the last look, else 0
+int take_async_error(HostSlot& s);
 // gsr_forward_ex with an explicit readback slot (nullptr = the calling thread's own).
 int forward_impl(const gsr_forward_args* args, HostSlot* slot);
 
@@ -235,6 +244,17 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     cfg.attrs = at; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 #endif
+}
+#endif
+
+// Raise the sticky error of a call from the device.  The word usually lives in mapped pinned HOST memory (HostSlot),
+// so this is a plain system-scope store + fence, not an atomic (idempotent: every reporter stores 1).
+#ifdef __CUDACC__
+__device__ __forceinline__ void gsr_raise_error(uint32_t* flag) {
+    if (flag) {
+        *reinterpret_cast<volatile uint32_t*>(flag) = 1u;
+        __threadfence_system();
+    }
 }
 #endif
 

@@ -66,6 +66,10 @@ constexpr int GROUP_SHIFT = 4;  // look-back groups of 16 tiles (16 * 6144 items
 constexpr int GROUP_TILES = 1 << GROUP_SHIFT;
 
 constexpr int HIST_THREADS = 256;
+// Look-back watchdog: polls (32 ns sleeps) a waiting digit thread tolerates before it gives up and raises the call's
+// sticky error (GSR_ERR_SORT_STALLED).  Tiles are ticketed, so a predecessor has always started; 2^22 polls = ~0.2 s.
+// -DGSR_FORCE_STALL: test build in which tile 1 of every pass reports a stall unconditionally (tests/test_gpu_stall.py).
+constexpr uint32_t WATCHDOG_SPINS = 1u << 22;
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -315,6 +319,9 @@ __device__ __forceinline__ void onesweep_tile(const PassArgs& a, const uint32_t 
     //    once all 16 tiles have arrived, its aggregate.
     {
         uint32_t excl = 0;
+#ifdef GSR_FORCE_STALL
+        if (tile == 1 && tid == 0) gsr_raise_error(a.error_flag);
+#endif
         if (tile != 0) {
             bool done = false;
             uint32_t spins = 0;
@@ -325,8 +332,8 @@ __device__ __forceinline__ void onesweep_tile(const PassArgs& a, const uint32_t 
                     if (done || t - w < gstart) break;
                     uint32_t v = look[w];
                     while ((v & FLAG_MASK) == 0) {  // predecessor has not published yet
-                        if (++spins > (1u << 22)) {  // watchdog: never expected to trip
-                            atomicExch(a.error_flag, 1u);
+                        if (++spins > WATCHDOG_SPINS) {  // never expected to trip; the frame is then invalid
+                            gsr_raise_error(a.error_flag);
                             v = FLAG_INC;
                             break;
                         }
@@ -370,8 +377,8 @@ __device__ __forceinline__ void onesweep_tile(const PassArgs& a, const uint32_t 
                             excl += g & 0xffffffu;
                             break;
                         }
-                        if (++spins > (1u << 22)) {
-                            atomicExch(a.error_flag, 1u);
+                        if (++spins > WATCHDOG_SPINS) {
+                            gsr_raise_error(a.error_flag);
                             done = true;
                             break;
                         }
@@ -544,7 +551,7 @@ size_t sort_temp_bytes(size_t n) {
 
 // ---- generic 64-bit-key sort (gsr_sort_pairs) ------------------------------------------------
 int launch_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, size_t n, int end_bit,
-                      char* temp, bool* result_in_a, cudaStream_t s, cudaEvent_t* events) {
+                      char* temp, bool* result_in_a, cudaStream_t s, cudaEvent_t* events, uint32_t* error_flag) {
     const int passes = sort_num_passes(end_bit);
     if (result_in_a) *result_in_a = (passes % 2) == 0;
     if (n == 0) return 0;
@@ -569,7 +576,7 @@ int launch_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint
         a.status = L.status + (size_t)ps * tiles * RADIX;
         a.gstat = L.gstat + (size_t)ps * num_groups(tiles) * RADIX;
         a.ticket = L.tickets + ps;
-        a.error_flag = L.tickets + MAX_PASSES;
+        a.error_flag = error_flag ? error_flag : L.tickets + MAX_PASSES;
         a.expand_low = nullptr; a.keys_out64 = nullptr;
         int rc = launch_pass<uint2, false, 2, ITEMS_LARGE>(a, s);
         if (rc < 0) return rc;
@@ -624,7 +631,7 @@ int launch_sort32(const Sort32Plan& p, cudaStream_t s, cudaEvent_t* events) {
         a.status = L.status + (size_t)ps * tiles * RADIX;
         a.gstat = L.gstat + (size_t)ps * num_groups(tiles) * RADIX;
         a.ticket = L.tickets + ps;
-        a.error_flag = L.tickets + MAX_PASSES;
+        a.error_flag = p.error_flag ? p.error_flag : L.tickets + MAX_PASSES;
         a.expand_low = nullptr; a.keys_out64 = nullptr;
         int rc;
         if (kept && ps == 0) {

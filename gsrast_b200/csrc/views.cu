@@ -29,20 +29,39 @@ constexpr int CAM_FLOATS = 36;  // view[16] proj[16] cam_pos[3] pad[1]
 struct Chunk {
     void* ptr = nullptr;
     size_t size = 0;
+    cudaStream_t stream = nullptr;  // the lane's stream: the only one that ever touches the chunk
 };
 
-// resizeFunctional (GSGaussians.cpp:27-42): grow-only, over-allocates 2x, same base otherwise.
+// resizeFunctional (GSGaussians.cpp:27-42): grow-only, over-allocates 2x, same base otherwise.  The reference grows
+// with cudaFree + cudaMalloc, i.e. a device-wide synchronisation in the middle of the frame; here the chunk is
+// stream-ordered memory of its lane (cudaFreeAsync / cudaMallocAsync), so growing one lane's chunk never stalls the
+// other lane.
 char* chunk_alloc(size_t n, void* user) {
     Chunk* c = static_cast<Chunk*>(user);
     if (n > c->size) {
-        if (c->ptr) cudaFree(c->ptr);
+        if (c->ptr) cudaFreeAsync(c->ptr, c->stream);
         c->ptr = nullptr;
         c->size = 0;
-        if (cudaMalloc(&c->ptr, 2 * n) != cudaSuccess) return nullptr;
+        if (cudaMallocAsync(&c->ptr, 2 * n, c->stream) != cudaSuccess) {
+            c->ptr = nullptr;
+            return nullptr;
+        }
         c->size = 2 * n;
     }
     return static_cast<char*>(c->ptr);
 }
+
+// Every entry point runs on the device the renderer was created on, whatever the caller's current device is.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
 
 struct Lane {
     cudaStream_t stream = nullptr;
@@ -68,6 +87,7 @@ struct Lane {
 }  // namespace
 
 struct Renderer {
+    int device = 0;
     int P, D, M, W, H;
     const float *means3D, *shs, *colors_precomp, *opacities, *scales, *rotations, *background;
     float scale_modifier;
@@ -83,6 +103,7 @@ namespace {
 
 int lane_init(Lane& l) {
     GSR_CUDA_TRY(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+    l.geom.stream = l.binning.stream = l.img.stream = l.stream;
     GSR_CUDA_TRY(cudaMalloc(&l.cam_dev, CAM_FLOATS * sizeof(float)));
     GSR_CUDA_TRY(cudaHostAlloc(&l.cam_host, CAM_FLOATS * sizeof(float), cudaHostAllocDefault));
     GSR_CUDA_TRY(cudaEventCreateWithFlags(&l.cam_free, cudaEventDisableTiming));
@@ -91,10 +112,10 @@ int lane_init(Lane& l) {
 }
 
 void lane_destroy(Lane& l) {
+    if (l.geom.ptr) cudaFreeAsync(l.geom.ptr, l.stream);
+    if (l.binning.ptr) cudaFreeAsync(l.binning.ptr, l.stream);
+    if (l.img.ptr) cudaFreeAsync(l.img.ptr, l.stream);
     if (l.stream) cudaStreamSynchronize(l.stream);
-    if (l.geom.ptr) cudaFree(l.geom.ptr);
-    if (l.binning.ptr) cudaFree(l.binning.ptr);
-    if (l.img.ptr) cudaFree(l.img.ptr);
     if (l.cam_dev) cudaFree(l.cam_dev);
     if (l.cam_host) cudaFreeHost(l.cam_host);
     if (l.copy_stream) cudaStreamSynchronize(l.copy_stream);
@@ -143,10 +164,10 @@ int render_one(Renderer* r, Lane& l, const float* cam36, float tan_fovx, float t
         a.rects = l.rects;
     }
     a.stream = l.stream;
-#ifndef GSR_RENDERER_LEAN
-#define GSR_RENDERER_LEAN 1
-#endif
-    a.flags = r->flags | (GSR_RENDERER_LEAN ? GSR_FLAG_LEAN_STATE : 0u);  // the lane's scratch is private: nobody can map cov3D / clamped
+    // the lane's scratch is private: unless the renderer was created with GSR_FLAG_KEEP_STATE (the Inspector's panel,
+    // gsr_renderer_map_geometry_state) nobody can read cov3D / clamped / tiles_touched / point_offsets, so they are skipped
+    a.flags = r->flags & ~GSR_FLAG_KEEP_STATE;
+    if (!(r->flags & GSR_FLAG_KEEP_STATE)) a.flags |= GSR_FLAG_LEAN_STATE;
     a.timings = times;
     return forward_impl(&a, &l.slot);
 }
@@ -211,6 +232,7 @@ extern "C" {
 void gsr_renderer_destroy(void* h) {
     Renderer* r = static_cast<Renderer*>(h);
     if (!r) return;
+    DeviceGuard guard(r->device);
     for (auto& l : r->lane) lane_destroy(l);
     if (r->ready) cudaEventDestroy(r->ready);
     delete r;
@@ -229,6 +251,10 @@ void* gsr_renderer_create(int P, int D, int M, const float* means3D, const float
     r->scale_modifier = scale_modifier; r->flags = flags;
     r->user_stream = static_cast<cudaStream_t>(stream);
     memset(&r->last, 0, sizeof(r->last));
+    if (cudaGetDevice(&r->device) != cudaSuccess) {
+        delete r;
+        return nullptr;
+    }
     bool ok = cudaEventCreateWithFlags(&r->ready, cudaEventDisableTiming) == cudaSuccess;
     for (auto& l : r->lane) ok = ok && lane_init(l) == 0;
     if (!ok) {
@@ -245,6 +271,7 @@ int gsr_renderer_render(void* h, const float* cameras, int n_views, float tan_fo
                         int* num_rendered, void* timings) {
     Renderer* r = static_cast<Renderer*>(h);
     if (!r || !cameras || !out_color || n_views < 0) return GSR_ERR_INVALID_ARG;
+    DeviceGuard guard(r->device);
     GSR_CUDA_TRY(cudaEventRecord(r->ready, r->user_stream));
     for (auto& l : r->lane) GSR_CUDA_TRY(cudaStreamWaitEvent(l.stream, r->ready, 0));
     const size_t frame = (size_t)3 * r->W * r->H;
@@ -272,51 +299,66 @@ int gsr_renderer_render(void* h, const float* cameras, int n_views, float tan_fo
 static int render_host_impl(Renderer* r, const float* cameras, int n_views, float tan_fovx, float tan_fovy,
                             void* out_host, bool u8, int* num_rendered) {
     if (!r || !cameras || !out_host || n_views < 0) return GSR_ERR_INVALID_ARG;
+    DeviceGuard guard(r->device);
     const size_t frame = (size_t)3 * r->W * r->H;
+    long long total = 0;
+    int err = 0;
+    // a failing CUDA call ends the loop; EVERY way out then drains both lanes, so no copy into the caller's buffer is
+    // still in flight when this function returns
+#define GSR_HOST_TRY(expr)                                    \
+    if (err == 0) {                                           \
+        cudaError_t e_ = (expr);                              \
+        if (e_ != cudaSuccess) err = -(int)e_;                \
+    }
     for (auto& l : r->lane) {
-        if (!l.copy_stream) GSR_CUDA_TRY(cudaStreamCreateWithFlags(&l.copy_stream, cudaStreamNonBlocking));
+        if (!l.copy_stream) GSR_HOST_TRY(cudaStreamCreateWithFlags(&l.copy_stream, cudaStreamNonBlocking));
         for (int b = 0; b < 2; ++b) {
-            if (!l.frame_dev[b]) GSR_CUDA_TRY(cudaMalloc(&l.frame_dev[b], frame * sizeof(float)));
-            if (u8 && !l.frame_u8[b]) GSR_CUDA_TRY(cudaMalloc(&l.frame_u8[b], frame));
-            if (!l.rendered[b]) GSR_CUDA_TRY(cudaEventCreateWithFlags(&l.rendered[b], cudaEventDisableTiming));
-            if (!l.copied[b]) GSR_CUDA_TRY(cudaEventCreateWithFlags(&l.copied[b], cudaEventDisableTiming));
+            if (!l.frame_dev[b]) GSR_HOST_TRY(cudaMalloc(&l.frame_dev[b], frame * sizeof(float)));
+            if (u8 && !l.frame_u8[b]) GSR_HOST_TRY(cudaMalloc(&l.frame_u8[b], frame));
+            if (!l.rendered[b]) GSR_HOST_TRY(cudaEventCreateWithFlags(&l.rendered[b], cudaEventDisableTiming));
+            if (!l.copied[b]) GSR_HOST_TRY(cudaEventCreateWithFlags(&l.copied[b], cudaEventDisableTiming));
         }
     }
-    GSR_CUDA_TRY(cudaEventRecord(r->ready, r->user_stream));
-    for (auto& l : r->lane) GSR_CUDA_TRY(cudaStreamWaitEvent(l.stream, r->ready, 0));
-    long long total = 0;
-    int rc_err = 0;
-    for (int v = 0; v < n_views && rc_err == 0; ++v) {
+    GSR_HOST_TRY(cudaEventRecord(r->ready, r->user_stream));
+    for (auto& l : r->lane) GSR_HOST_TRY(cudaStreamWaitEvent(l.stream, r->ready, 0));
+    for (int v = 0; v < n_views && err == 0; ++v) {
         Lane& l = r->lane[v % LANES];
         const int b = l.frame_ix;
         l.frame_ix ^= 1;
         // the frame buffer is free again once the copy issued from it two views ago has drained
-        if (l.copy_pending[b]) GSR_CUDA_TRY(cudaStreamWaitEvent(l.stream, l.copied[b], 0));
+        if (l.copy_pending[b]) GSR_HOST_TRY(cudaStreamWaitEvent(l.stream, l.copied[b], 0));
+        if (err) break;
         int rc = render_one(r, l, cameras + (size_t)v * CAM_FLOATS, tan_fovx, tan_fovy, l.frame_dev[b], nullptr);
-        if (rc < 0) { rc_err = rc; break; }
+        if (rc < 0) { err = rc; break; }
         if (u8) {
             int rq = launch_quantize_u8(l.frame_dev[b], l.frame_u8[b], frame, l.stream);
-            if (rq < 0) { rc_err = rq; break; }
+            if (rq < 0) { err = rq; break; }
         }
-        GSR_CUDA_TRY(cudaEventRecord(l.rendered[b], l.stream));
-        GSR_CUDA_TRY(cudaStreamWaitEvent(l.copy_stream, l.rendered[b], 0));
-        if (u8)
-            GSR_CUDA_TRY(cudaMemcpyAsync(static_cast<unsigned char*>(out_host) + (size_t)v * frame, l.frame_u8[b], frame,
+        GSR_HOST_TRY(cudaEventRecord(l.rendered[b], l.stream));
+        GSR_HOST_TRY(cudaStreamWaitEvent(l.copy_stream, l.rendered[b], 0));
+        if (u8) {
+            GSR_HOST_TRY(cudaMemcpyAsync(static_cast<unsigned char*>(out_host) + (size_t)v * frame, l.frame_u8[b], frame,
                                          cudaMemcpyDeviceToHost, l.copy_stream));
-        else
-            GSR_CUDA_TRY(cudaMemcpyAsync(static_cast<float*>(out_host) + (size_t)v * frame, l.frame_dev[b],
+        } else {
+            GSR_HOST_TRY(cudaMemcpyAsync(static_cast<float*>(out_host) + (size_t)v * frame, l.frame_dev[b],
                                          frame * sizeof(float), cudaMemcpyDeviceToHost, l.copy_stream));
-        GSR_CUDA_TRY(cudaEventRecord(l.copied[b], l.copy_stream));
-        l.copy_pending[b] = true;
+        }
+        GSR_HOST_TRY(cudaEventRecord(l.copied[b], l.copy_stream));
+        if (err == 0) l.copy_pending[b] = true;
         if (num_rendered) num_rendered[v] = rc;
         total += rc;
     }
+#undef GSR_HOST_TRY
     for (auto& l : r->lane) {
-        GSR_CUDA_TRY(cudaStreamSynchronize(l.copy_stream));
-        GSR_CUDA_TRY(cudaStreamSynchronize(l.stream));
+        cudaError_t e1 = l.copy_stream ? cudaStreamSynchronize(l.copy_stream) : cudaSuccess;
+        cudaError_t e2 = cudaStreamSynchronize(l.stream);
+        if (err == 0 && e1 != cudaSuccess) err = -(int)e1;
+        if (err == 0 && e2 != cudaSuccess) err = -(int)e2;
         l.copy_pending[0] = l.copy_pending[1] = false;
+        const int ea = take_async_error(l.slot);  // both lanes are idle: every watchdog of this batch has reported
+        if (err == 0 && ea < 0) err = ea;
     }
-    if (rc_err) return rc_err;
+    if (err) return err;
     return (int)(total > 0x7fffffffLL ? 0x7fffffff : total);
 }
 
@@ -341,6 +383,16 @@ int gsr_renderer_last_times(void* h, gsr_stage_times* out) {
     Renderer* r = static_cast<Renderer*>(h);
     if (!r || !out) return GSR_ERR_INVALID_ARG;
     *out = r->last;
+    return 0;
+}
+
+int gsr_renderer_num_lanes(void) { return LANES; }
+
+// GSGaussians::mapGeometryState (GSGaussians.cpp:214-219): fromChunk over the lane's geometry chunk.
+int gsr_renderer_map_geometry_state(void* h, int lane, gsr_geometry_state* out) {
+    Renderer* r = static_cast<Renderer*>(h);
+    if (!r || !out || lane < 0 || lane >= LANES || !r->lane[lane].geom.ptr) return GSR_ERR_INVALID_ARG;
+    gsr_geometry_state_map(static_cast<char*>(r->lane[lane].geom.ptr), r->P, out);
     return 0;
 }
 

@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import FLAG_BLEND_SIMPLE, FLAG_GSRAST_COMPAT  # noqa: F401
+from ._lib import FLAG_BLEND_COUNT, FLAG_BLEND_SIMPLE, FLAG_GSRAST_COMPAT  # noqa: F401
 
 NUM_CHANNELS = 3  # Config.hpp:46
 BLOCK_X = 16      # Config.hpp:47
@@ -169,8 +169,9 @@ def _forward(geometryBuffer, binningBuffer, imageBuffer, P, D, M, background, wi
         return a.ctypes.data
 
     times = _lib.StageTimes() if timings else None
+    dev = out_color.device if isinstance(out_color, torch.Tensor) else None
     if stream is None:
-        stream_ptr = torch.cuda.current_stream().cuda_stream
+        stream_ptr = torch.cuda.current_stream(dev).cuda_stream
     else:
         stream_ptr = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
     a = _lib.ForwardArgs(
@@ -184,7 +185,12 @@ def _forward(geometryBuffer, binningBuffer, imageBuffer, P, D, M, background, wi
         out_color=_ptr(out_color), radii=_ptr(radii), rects=_ptr(rects), boxmin=host3(boxmin), boxmax=host3(boxmax),
         stream=stream_ptr, flags=int(flags),
         timings=C.pointer(times) if times is not None else None)
-    rc = L.gsr_forward_ex(C.byref(a))
+    # the library works on the CURRENT device (streams, events, the pinned read-back slot): make it the tensors'
+    if dev is not None and dev.type == "cuda":
+        with torch.cuda.device(dev):
+            rc = L.gsr_forward_ex(C.byref(a))
+    else:
+        rc = L.gsr_forward_ex(C.byref(a))
     _lib.check(rc)
     if timings:
         return rc, times.as_dict()

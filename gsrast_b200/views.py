@@ -17,6 +17,18 @@ import torch
 from . import _lib
 
 
+def _tensor_from_ptr(addr: int, nbytes: int, device) -> torch.Tensor:
+    """uint8 tensor over `nbytes` of device memory owned by the native library (no copy; valid while the owner lives)."""
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(addr), False), "version": 2}
+    with torch.cuda.device(device):
+        return torch.as_tensor(h, device=device)
+
+
 def pack_cameras(cameras) -> np.ndarray:
     """list[Camera] -> float32 [n,36] (view[16] proj[16] cam_pos[3] pad): the per-frame upload of
     GSGaussians::draw (GSGaussians.cpp:171-173)."""
@@ -66,19 +78,45 @@ def views_per_rank(n_views: int, world_size: int) -> int:
 
 class ViewRenderer:
     def __init__(self, *, P, D, M, means3D, shs, colors_precomp, opacities, scales, rotations, background, width,
-                 height, scale_modifier=1.0, compat=False, flags=0, stream=None):
+                 height, scale_modifier=1.0, compat=False, flags=0, stream=None, keep_state=False):
+        """keep_state: GSR_FLAG_KEEP_STATE — every geometry-state field stays materialised so that
+        `map_geometry_state` serves the Inspector's panel (Inspector.cpp:174-188); default is the lean state."""
         self._keep = (means3D, shs, colors_precomp, opacities, scales, rotations, background)
         self.width, self.height = int(width), int(height)
         self.device = means3D.device
+        self.P = int(P)
         p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
         self._stream = stream
         sp = (stream.cuda_stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream)
-        fl = int(flags) | (_lib.FLAG_GSRAST_COMPAT if compat else 0)
-        self._h = _lib.lib().gsr_renderer_create(int(P), int(D), int(M), p(means3D), p(shs), p(colors_precomp),
-                                                 p(opacities), p(scales), p(rotations), p(background),
-                                                 float(scale_modifier), self.width, self.height, sp, fl)
+        fl = int(flags) | (_lib.FLAG_GSRAST_COMPAT if compat else 0) | (_lib.FLAG_KEEP_STATE if keep_state else 0)
+        # the native renderer binds to the CURRENT device: make that the tensors' device, not whatever torch's default is
+        with torch.cuda.device(self.device):
+            self._h = _lib.lib().gsr_renderer_create(int(P), int(D), int(M), p(means3D), p(shs), p(colors_precomp),
+                                                     p(opacities), p(scales), p(rotations), p(background),
+                                                     float(scale_modifier), self.width, self.height, sp, fl)
         if not self._h:
             raise RuntimeError("gsr_renderer_create failed")
+
+    def map_geometry_state(self, lane: int = 0) -> dict:
+        """mapGeometryState (GSGaussians.cpp:214-219) over the renderer's private scratch: zero-copy views of the nine
+        reference fields of `lane` (view v of a call ran on lane v % num_lanes; with timings, lane 0)."""
+        st = _lib.GeometryState()
+        _lib.check(_lib.lib().gsr_renderer_map_geometry_state(self._h, int(lane), C.byref(st)))
+        P = self.P
+
+        def view(addr, nbytes, dtype, shape):
+            return _tensor_from_ptr(addr, nbytes, self.device).view(dtype).view(*shape)
+
+        f32, i32, u8 = torch.float32, torch.int32, torch.uint8
+        return dict(depths=view(st.depths, 4 * P, f32, (P,)), clamped=view(st.clamped, 3 * P, u8, (P, 3)),
+                    internal_radii=view(st.internal_radii, 4 * P, i32, (P,)), means2D=view(st.means2D, 8 * P, f32, (P, 2)),
+                    cov3D=view(st.cov3D, 24 * P, f32, (P, 6)), conic_opacity=view(st.conic_opacity, 16 * P, f32, (P, 4)),
+                    rgb=view(st.rgb, 12 * P, f32, (P, 3)), tiles_touched=view(st.tiles_touched, 4 * P, i32, (P,)),
+                    point_offsets=view(st.point_offsets, 4 * P, i32, (P,)))
+
+    @staticmethod
+    def num_lanes() -> int:
+        return int(_lib.lib().gsr_renderer_num_lanes())
 
     @classmethod
     def from_scene(cls, scene, width, height, device="cuda", background=(0.0, 0.0, 0.0), **kw):

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define GSR_VERSION 100 /* round 1 */
+#define GSR_VERSION 200 /* round 2 */
 
 /* Scratch allocator callback: the C form of the reference's std::function<char*(size_t)>
  * (apps/gsrast/gscuda/GSCuda.cuh:103-105; resizeFunctional, GSGaussians.cpp:27-42).
@@ -46,10 +46,21 @@ typedef char* (*gsr_alloc_fn)(size_t bytes, void* user);
                                        GSCuda.cu:445).  gsr_renderer_* sets it for its private per-lane scratch;
                                        gsr_forward* never does on its own */
 
+#define GSR_FLAG_BLEND_COUNT 0x10u  /* with `timings`: run the counting instantiation of the blend kernel (same arithmetic)
+                                       and return its work counters in gsr_stage_times.blend_counters — the unit
+                                       SURVEY 8(d) rates the blend in.  Slower; for reporting, never on a timed path */
+#define GSR_FLAG_KEEP_STATE 0x20u   /* gsr_renderer_create only: keep every geometry-state field materialised (no
+                                       GSR_FLAG_LEAN_STATE) so gsr_renderer_map_geometry_state serves the reference's
+                                       Inspector panel (apps/gsrast/Inspector.cpp:174-188) */
+
 #define GSR_ERR_INVALID_ARG (-1000)
 #define GSR_ERR_ALLOC_FAILED (-1001)   /* an allocator callback returned NULL */
-#define GSR_ERR_TOO_MANY_PAIRS (-1002) /* num_rendered >= 2^30: beyond the sort's look-back counters */
-#define GSR_ERR_SORT_STALLED (-1003)   /* internal watchdog tripped (never expected) */
+#define GSR_ERR_TOO_MANY_PAIRS (-1002) /* num_rendered >= 2^30: beyond the sort's look-back counters (detected on the
+                                          device with a 64-bit sum, so a wrapped 32-bit total cannot slip through) */
+#define GSR_ERR_SORT_STALLED (-1003)   /* a look-back watchdog tripped (never expected).  Asynchronous like a CUDA
+                                          error: reported by the call that notices it — the same call when it
+                                          synchronises (timings, *_render_host*), otherwise the next call of the same
+                                          host thread / renderer.  The frame that stalled is invalid. */
 #define GSR_ERR_PLY_OPEN (-1004)       /* the file cannot be opened ("Bad PLY reader", SplatData.cpp:120-124) */
 #define GSR_ERR_PLY_FORMAT (-1005)     /* no vertex count on the third header line / no end_header */
 #define GSR_ERR_PLY_TRUNCATED (-1006)  /* fewer than P records in the body ("Reader is EOF?", SplatData.cpp:146-152) */
@@ -108,7 +119,13 @@ typedef struct gsr_stage_times {
     int binning_mode;       /* 0 = bin expansion, 1 = radix passes over the pairs */
     float expand_count_ms;  /* expand_count_kernel alone (one launch) */
     float expand_fill_ms;   /* expand_fill_kernel alone (one launch): the pass that writes the 12 B/pair result */
+    /* GSR_FLAG_BLEND_COUNT: [0] tile-rounds staged (128 splats each), [1] warp-rounds that walked a candidate list,
+     * [2] candidates listed (warp x splat), [3] candidate trips executed (warp x splat; x32 = evaluated pixel-splat
+     * pairs, the unit of SURVEY 8(d)), [4] of those pairs, the ones whose pixel was still live, [5] pairs that passed
+     * the power / alpha tests, [6] pairs blended, [7] splats staged */
+    unsigned long long blend_counters[8];
 } gsr_stage_times;
+#define GSR_BLEND_COUNTERS 8
 
 /* Same call with explicit strides / flags (superset of the two above). */
 typedef struct gsr_forward_args {
@@ -177,6 +194,7 @@ typedef struct gsr_image_state {
     uint32_t* n_contrib;  /* [W*H] */
     float* accum_alpha;   /* [W*H] final transmittance */
     uint32_t* tile_order; /* [tiles] scratch: per-tile pair counts, then their exclusive scan (bin expansion) */
+    unsigned long long* blend_counters; /* [GSR_BLEND_COUNTERS] work counters of the blend (GSR_FLAG_BLEND_COUNT) */
 } gsr_image_state;
 
 typedef struct gsr_binning_state {
@@ -244,6 +262,14 @@ int gsr_renderer_render_host_u8(void* renderer, const float* cameras, int n_view
                                 unsigned char* out_color_host, int* num_rendered);
 int gsr_frames_to_u8(const float* frames, unsigned char* out, size_t n_values, void* stream);
 int gsr_renderer_last_times(void* renderer, gsr_stage_times* out);
+/* The renderer's form of GSGaussians::mapGeometryState (apps/gsrast/GSGaussians.cpp:214-219): field pointers into the
+ * private geometry chunk of `lane` (view v of a render call ran on lane v % gsr_renderer_num_lanes(); with `timings`
+ * every view runs on lane 0).  Valid until the next render call on that renderer; synchronise the renderer's stream
+ * before reading.  The renderer must have been created with GSR_FLAG_KEEP_STATE for cov3D / clamped / tiles_touched /
+ * point_offsets to hold data (otherwise those four are stale scratch).  Returns 0, or GSR_ERR_INVALID_ARG when the
+ * lane has not rendered yet. */
+int gsr_renderer_map_geometry_state(void* renderer, int lane, gsr_geometry_state* out);
+int gsr_renderer_num_lanes(void);
 
 /* One-shot device repack of the buffers GSRast's viewer uploads (vec4 means / scales,
  * apps/gsrast/GSGaussians.cpp:121-125; SH in raw PLY order, SplatData.hpp:17-25 — f_dc[3]

@@ -31,7 +31,7 @@ def test_header_symbols_exported(L):
     for sym in sorted(declared):
         assert hasattr(L, sym), "libgsrast_b200.so does not export %s" % sym
     assert declared == set(_lib.EXPORTS)
-    assert L.gsr_version() == 100
+    assert L.gsr_version() == 200
 
 
 def test_cpp_shim_headers_present():

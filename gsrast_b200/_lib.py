@@ -106,6 +106,7 @@ EXPORTS = (
     "gsr_renderer_create", "gsr_renderer_destroy", "gsr_renderer_render", "gsr_renderer_render_host",
     "gsr_renderer_last_times", "gsr_repack_gsrast_scene", "gsr_ply_count", "gsr_ply_load",
     "gsr_renderer_render_host_u8", "gsr_frames_to_u8", "gsr_renderer_map_geometry_state", "gsr_renderer_num_lanes",
+    "gsr_pinned_alloc", "gsr_pinned_free",
 )
 
 _lib = None
@@ -179,6 +180,10 @@ def lib():
     L.gsr_renderer_map_geometry_state.argtypes = [C.c_void_p, C.c_int, C.POINTER(GeometryState)]
     L.gsr_renderer_num_lanes.restype = C.c_int
     L.gsr_renderer_num_lanes.argtypes = []
+    L.gsr_pinned_alloc.restype = C.c_void_p
+    L.gsr_pinned_alloc.argtypes = [C.c_size_t, C.c_uint]
+    L.gsr_pinned_free.restype = None
+    L.gsr_pinned_free.argtypes = [C.c_void_p]
     L.gsr_ply_count.restype = C.c_int
     L.gsr_ply_count.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
     L.gsr_ply_load.restype = C.c_int

@@ -161,7 +161,7 @@ size_t gsr_geometry_state_map(char* chunk, int P, gsr_geometry_state* g) {
     st.scan_size = ((size_t)num_pre_blocks(P) + 4) * sizeof(uint32_t);
     obtain(c, st.block_sums, st.scan_size);
     obtain(c, st.point_offsets, n * sizeof(uint32_t));
-    obtain(c, st.depth_keys, n * sizeof(uint32_t));
+    st.depth_keys = reinterpret_cast<uint32_t*>(st.depths);  // the same array: see gsrast_b200.h
     obtain(c, st.tile_rects, n * 2 * sizeof(uint32_t));
     for (int i = 0; i < 2; ++i) obtain(c, st.depth_sort_keys[i], n * sizeof(uint32_t));
     for (int i = 0; i < 2; ++i) obtain(c, st.depth_sort_ids[i], n * sizeof(uint32_t));
@@ -300,7 +300,7 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         pp.radii = radii; pp.rects = a->rects; pp.depths = geom.depths; pp.clamped = geom.clamped;
         pp.means2D = geom.means2D; pp.cov3D = geom.cov3D; pp.conic_opacity = geom.conic_opacity;
         pp.rgb = geom.rgb; pp.tiles_touched = geom.tiles_touched; pp.block_sums = geom.block_sums;
-        pp.depth_keys = geom.depth_keys; pp.tile_rects = geom.tile_rects;
+        pp.tile_rects = geom.tile_rects;
         pp.coarse_block_sums = bin_mode ? geom.coarse_block_sums : nullptr;
         const bool lean = (a->flags & GSR_FLAG_LEAN_STATE) != 0;
         if (lean) { pp.cov3D = nullptr; pp.clamped = nullptr; pp.tiles_touched = nullptr; }

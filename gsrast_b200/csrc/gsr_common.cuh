@@ -52,7 +52,7 @@ struct PreprocessParams {
     // outputs
     int* radii;
     int* rects;  // int2[P] or null
-    float* depths;
+    float* depths;  // [P]; doubles as the low half of the sort key: 0xffffffff where nothing is emitted
     unsigned char* clamped;
     float* means2D;
     float* cov3D;
@@ -61,7 +61,6 @@ struct PreprocessParams {
     uint32_t* tiles_touched;
     uint32_t* block_sums;  // [ceil(P/256)]
     uint32_t* coarse_block_sums;  // [ceil(P/256)] (Gaussian, bin) records of the block, or null
-    uint32_t* depth_keys;  // [P] low half of the sort key: depth bits, 0xffffffff when nothing is emitted
     uint32_t* tile_rects;  // uint2[P]: (miny<<16|minx, height<<16|width) of the tile rect, 0 when nothing is emitted
 };
 

@@ -183,14 +183,32 @@ __global__ void __launch_bounds__(PRE_THREADS, GSR_PRE_MINB) preprocess_kernel(c
         }
 
         // The SH block of a Gaussian that passed the frustum test is needed ~200 instructions from now (after
-        // the covariance math and the warp compaction): start pulling its two 128-byte lines into L2.
-        // Only for centres on or near the screen (a hint: an off-screen centre with a huge radius just misses).
-        if (!COMPAT && alive && p.colors_precomp == nullptr && fabsf(prx) < 1.25f && fabsf(pry) < 1.25f) {
+        // the covariance math and the warp compaction): start pulling it into L2.  Only for centres on the screen
+        // (GSR_PRE_PREFETCH_BOUND in NDC; a hint: an off-screen centre whose radius reaches the screen just misses) —
+        // at 1.25 the Gaussians of the band around the screen, which are culled a moment later, cost ~35 MB of SH reads
+        // per C2 frame.  GSR_PRE_PREFETCH_MODE 1: only the 128-byte line the 192-byte block owns entirely (the other
+        // 64 bytes share their line with a neighbour that may be culled; they arrive with the demand loads);
+        // 0: both lines; 2: no prefetch.
+#ifndef GSR_PRE_PREFETCH_BOUND
+#define GSR_PRE_PREFETCH_BOUND 1.03f
+#endif
+#ifndef GSR_PRE_PREFETCH_MODE
+#define GSR_PRE_PREFETCH_MODE 1
+#endif
+        if (!COMPAT && GSR_PRE_PREFETCH_MODE != 2 && alive && p.colors_precomp == nullptr &&
+            fabsf(prx) < GSR_PRE_PREFETCH_BOUND && fabsf(pry) < GSR_PRE_PREFETCH_BOUND) {
             const char* shp = reinterpret_cast<const char*>(p.shs + (size_t)idx * p.M * 3);
-            // (cp.async.bulk.prefetch.L2 of exactly the block's 192 bytes was tried instead of two line prefetches:
+            // (cp.async.bulk.prefetch.L2 of exactly the block's 192 bytes was tried instead of line prefetches:
             // preprocess 0.169 -> 0.190 ms, profiles/r01f_ab.txt)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(shp));
-            if (p.M * 12 > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(shp + 128));
+            if (GSR_PRE_PREFETCH_MODE == 0 || p.M * 12 <= 128) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(shp));
+                if (p.M * 12 > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(shp + 128));
+            } else {
+                // the block starts on a 64-byte boundary (M = 16: 192 * idx): its first 128 bytes are a whole line when
+                // the start is 128-aligned, otherwise its last 128 bytes are
+                const uintptr_t a = reinterpret_cast<uintptr_t>(shp);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"((a & 127u) ? shp + (size_t)p.M * 12 - 128 : shp));
+            }
         }
 
         float cov00 = 0.f, cov01 = 0.f, cov11 = 0.f;
@@ -361,7 +379,9 @@ __global__ void __launch_bounds__(PRE_THREADS, GSR_PRE_MINB) preprocess_kernel(c
         // depth / mean / conic are stored for EVERY Gaussian (zeros where nothing is emitted; the reference leaves
         // those entries stale): whole sectors are written, so the memory system never has to read a sector back to
         // merge a few surviving 4..16-byte records into it (measured: ~130 MB of DRAM reads per C2 frame)
-        p.depths[idx] = o_depth;
+        // depths doubles as the low half of the sort key (GSCuda.cu:466-471): Gaussians that emit nothing carry the
+        // all-ones pattern there, which the depth sort drops (the reference leaves their entry stale)
+        p.depths[idx] = tiles ? o_depth : __uint_as_float(0xffffffffu);
         reinterpret_cast<float2*>(p.means2D)[idx] = o_xy;
         reinterpret_cast<float4*>(p.conic_opacity)[idx] = o_conic;
         if (tiles == 0 && p.colors_precomp == nullptr) {
@@ -374,8 +394,6 @@ __global__ void __launch_bounds__(PRE_THREADS, GSR_PRE_MINB) preprocess_kernel(c
         }
         p.radii[idx] = radius_out;
         if (p.tiles_touched) p.tiles_touched[idx] = tiles;
-        // low half of the sort key (GSCuda.cu:466-471); Gaussians that emit nothing sort last
-        p.depth_keys[idx] = tiles ? __float_as_uint(depth) : 0xffffffffu;
         reinterpret_cast<uint2*>(p.tile_rects)[idx] = rec;
     }
 

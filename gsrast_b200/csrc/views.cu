@@ -388,6 +388,19 @@ int gsr_renderer_last_times(void* h, gsr_stage_times* out) {
 
 int gsr_renderer_num_lanes(void) { return LANES; }
 
+void* gsr_pinned_alloc(size_t bytes, unsigned flags) {
+    void* p = nullptr;
+    unsigned f = cudaHostAllocDefault;
+    if (flags & GSR_PINNED_WRITE_COMBINED) f |= cudaHostAllocWriteCombined;
+    if (flags & GSR_PINNED_PORTABLE) f |= cudaHostAllocPortable;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, f) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void gsr_pinned_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 // GSGaussians::mapGeometryState (GSGaussians.cpp:214-219): fromChunk over the lane's geometry chunk.
 int gsr_renderer_map_geometry_state(void* h, int lane, gsr_geometry_state* out) {
     Renderer* r = static_cast<Renderer*>(h);

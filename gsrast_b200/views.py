@@ -29,6 +29,31 @@ def _tensor_from_ptr(addr: int, nbytes: int, device) -> torch.Tensor:
         return torch.as_tensor(h, device=device)
 
 
+class PinnedFrames:
+    """Page-locked host landing buffer [n,3,H,W] from gsr_pinned_alloc (optionally write-combined); `.tensor` is a
+    CPU tensor over it.  Keep the object alive while the tensor is in use."""
+
+    def __init__(self, shape, dtype=torch.float32, write_combined=False):
+        self.nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        self.ptr = _lib.lib().gsr_pinned_alloc(self.nbytes, (1 if write_combined else 0) | 2)
+        if not self.ptr:
+            raise MemoryError("gsr_pinned_alloc(%d) failed" % self.nbytes)
+        raw = (C.c_ubyte * self.nbytes).from_address(self.ptr)
+        self.tensor = torch.frombuffer(raw, dtype=torch.uint8).view(dtype).view(*shape)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.tensor = None
+            _lib.lib().gsr_pinned_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def pack_cameras(cameras) -> np.ndarray:
     """list[Camera] -> float32 [n,36] (view[16] proj[16] cam_pos[3] pad): the per-frame upload of
     GSGaussians::draw (GSGaussians.cpp:171-173)."""

@@ -166,7 +166,8 @@ int gsr_forward_ex(const gsr_forward_args* args);
  * AuxBuffer.cuh:36-78); the Inspector reads nine geometry fields that way
  * (GSGaussians.cpp:214-219, Inspector.cpp:174-188).  These are the equivalents. */
 typedef struct gsr_geometry_state {
-    float* depths;            /* [P] */
+    float* depths;            /* [P]; entries of Gaussians that emit no pair hold the bit pattern 0xffffffff (the
+                                 reference leaves them stale, GSCuda.cu:356-359 returns before :369) */
     unsigned char* clamped;   /* [3P] */
     int* internal_radii;      /* [P] */
     float* means2D;           /* [P][2] */
@@ -178,7 +179,8 @@ typedef struct gsr_geometry_state {
     uint32_t* block_sums;     /* scan scratch (replaces the CUB temp storage) */
     size_t scan_size;
     /* depth half of the radix sort, run per Gaussian before duplication */
-    uint32_t* depth_keys;        /* [P] depth bits; 0xffffffff for Gaussians that emit no pair */
+    uint32_t* depth_keys;        /* = (uint32_t*)depths: the low half of the sort key is the depth's bit pattern, so the
+                                    depth sort reads that array directly (no second 4 B/Gaussian store) */
     uint32_t* tile_rects;        /* [P][2] miny<<16|minx, height<<16|width of the tile rect (0 = emits nothing) */
     uint32_t* depth_sort_keys[2];/* [P] ping-pong; [1] ends up holding the sorted depth keys */
     uint32_t* depth_sort_ids[2]; /* [P] ping-pong; [1] ends up holding the Gaussian ids in depth order */
@@ -261,6 +263,14 @@ int gsr_renderer_render_host(void* renderer, const float* cameras, int n_views, 
 int gsr_renderer_render_host_u8(void* renderer, const float* cameras, int n_views, float tan_fovx, float tan_fovy,
                                 unsigned char* out_color_host, int* num_rendered);
 int gsr_frames_to_u8(const float* frames, unsigned char* out, size_t n_values, void* stream);
+/* Page-locked HOST landing buffers for the *_render_host* calls (the reference keeps its frame in a GL buffer,
+ * apps/gsrast/CudaBuffer.cpp:21-32; a host-side consumer needs pinned memory for the copies to overlap rendering).
+ * GSR_PINNED_WRITE_COMBINED: not snooped during the device's writes and slow to READ from the CPU — for frames that
+ * are forwarded (network, encoder DMA), not inspected.  Returns NULL on failure. */
+#define GSR_PINNED_WRITE_COMBINED 0x1u
+#define GSR_PINNED_PORTABLE 0x2u
+void* gsr_pinned_alloc(size_t bytes, unsigned flags);
+void gsr_pinned_free(void* ptr);
 int gsr_renderer_last_times(void* renderer, gsr_stage_times* out);
 /* The renderer's form of GSGaussians::mapGeometryState (apps/gsrast/GSGaussians.cpp:214-219): field pointers into the
  * private geometry chunk of `lane` (view v of a render call ran on lane v % gsr_renderer_num_lanes(); with `timings`

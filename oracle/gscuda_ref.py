@@ -11,8 +11,10 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libgscuda_ref.so")
+# the same sources built with the reference's own flags (nvcc's default FMA contraction): report-only variant
+LIB_PATH_FMAD = os.path.join(_HERE, "_ref", "libgscuda_ref_fmad.so")
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_void_p)
-_lib = None
+_libs = {}
 
 
 class _Geom(C.Structure):
@@ -28,14 +30,14 @@ class _Img(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in ("ranges", "nContrib", "accumAlpha", "total")]
 
 
-def available() -> bool:
-    return os.path.exists(LIB_PATH)
+def available(fmad: bool = False) -> bool:
+    return os.path.exists(LIB_PATH_FMAD if fmad else LIB_PATH)
 
 
-def lib():
-    global _lib
+def lib(fmad: bool = False):
+    _lib = _libs.get(fmad)
     if _lib is None:
-        _lib = C.CDLL(LIB_PATH)
+        _lib = _libs[fmad] = C.CDLL(LIB_PATH_FMAD if fmad else LIB_PATH)
         _lib.gscuda_ref_forward.restype = None
         _lib.gscuda_ref_forward.argtypes = [ALLOC_FN, C.c_void_p, ALLOC_FN, C.c_void_p, ALLOC_FN, C.c_void_p, C.c_int,
                                             C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
@@ -52,10 +54,11 @@ class RefRenderer:
     """Holds the viewer-layout device buffers and the grow-only allocators like GSGaussians does
     (GSGaussians.cpp:27-42,109-153) and calls the reference's gscuda::forward."""
 
-    def __init__(self, scene, width, height, device="cuda", use_rects=True):
+    def __init__(self, scene, width, height, device="cuda", use_rects=True, fmad=False):
         import torch
 
         self.torch = torch
+        self.lib = lib(fmad)
         self.dev = torch.device(device)
         self.W, self.H, self.P = width, height, scene.P
         means4, scales4, rot, opac, shs_raw = scene.gsrast_layout()
@@ -89,7 +92,7 @@ class RefRenderer:
         cpos = torch.from_numpy(cam.cam_pos).to(self.dev)
         torch.cuda.synchronize()
         p = lambda x: None if x is None else x.data_ptr()  # noqa: E731
-        lib().gscuda_ref_forward(self.cbs[0], None, self.cbs[1], None, self.cbs[2], None, self.P, 3, 16, p(self.bg),
+        self.lib.gscuda_ref_forward(self.cbs[0], None, self.cbs[1], None, self.cbs[2], None, self.P, 3, 16, p(self.bg),
                                  self.W, self.H, p(self.means), p(self.shs), p(self.colors), p(self.opac),
                                  p(self.scales), 1.0, p(self.rot), None, p(view), p(proj), p(cpos), cam.tan_fovx,
                                  cam.tan_fovy, 0, p(self.out), None, p(self.rects), None, None)
@@ -102,7 +105,7 @@ class RefRenderer:
         P, N = self.P, self.W * self.H
         g = _Geom()
         gb = self.bufs[0]
-        lib().gscuda_ref_geometry_layout(gb.data_ptr(), P, C.byref(g))
+        self.lib.gscuda_ref_geometry_layout(gb.data_ptr(), P, C.byref(g))
 
         def view(buf, off, nbytes, dt):
             rel = off
@@ -120,14 +123,14 @@ class RefRenderer:
         if R > 0:
             b = _Bin()
             bb = self.bufs[1]
-            lib().gscuda_ref_binning_layout(bb.data_ptr(), R, C.byref(b))
+            self.lib.gscuda_ref_binning_layout(bb.data_ptr(), R, C.byref(b))
             out["keys_unsorted"] = view(bb, b.keysUnsorted, 8 * R, np.uint64)
             out["keys"] = view(bb, b.keys, 8 * R, np.uint64)
             out["values_unsorted"] = view(bb, b.valuesUnsorted, 4 * R, np.uint32)
             out["values"] = view(bb, b.values, 4 * R, np.uint32)
         im = _Img()
         ib = self.bufs[2]
-        lib().gscuda_ref_image_layout(ib.data_ptr(), N, C.byref(im))
+        self.lib.gscuda_ref_image_layout(ib.data_ptr(), N, C.byref(im))
         T = ((self.W + 15) // 16) * ((self.H + 15) // 16)
         out["ranges"] = view(ib, im.ranges, 8 * T, np.uint32).reshape(T, 2)  # the reference sizes it per pixel
         out["n_contrib"] = view(ib, im.nContrib, 4 * N, np.uint32)

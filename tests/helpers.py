@@ -35,7 +35,7 @@ def run_cuda(scene, cam, *, compat=False, use_rects=False, D=None, flags=0, back
                                    max(scene.max_coeffs, 1), bg, W, H, keep[0], keep[1], keep[5], keep[2], keep[3],
                                    1.0, keep[4], keep[6], view, proj, cpos, cam.tan_fovx, cam.tan_fovy, False,
                                    out_color, radii, rects, boxmin, boxmax, flags=flags, timings=timings)
-    torch.cuda.synchronize()
+    torch.cuda.synchronize(dev)
     times = None
     if timings:
         res, times = res

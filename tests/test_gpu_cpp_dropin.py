@@ -83,3 +83,26 @@ def test_cpp_views_host_ply_to_u8_frames(tmp_path):
     assert np.array_equal(frames, want.numpy())
     assert frames.max() > 0
     vr.close()
+
+
+def test_cpp_interop_stream_ordering_and_inspector_state(tmp_path):
+    """tests/cpp/interop_host.cpp: a caller-owned NON-default stream and output buffer, a racing memset queued before
+    the render and a D2H copy queued right after it with no synchronisation in between (INTEGRATION.md option C); and
+    the Inspector's fields read through gsr_renderer_map_geometry_state on a GSR_FLAG_KEEP_STATE renderer."""
+    from gsrast_b200.views import pack_cameras
+
+    exe = os.path.join(ROOT, "tests", "cpp", "interop_host")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.dirname(exe), "interop_host"])
+    sc = S.make_config_scene("C1", P=60_000)[0]
+    W, H = 960, 540
+    cams = Cm.orbit_cameras(5, W, H)
+    ply, cam_bin = str(tmp_path / "data.ply"), str(tmp_path / "cams.bin")
+    S.write_ply(ply, sc)
+    with open(cam_bin, "wb") as f:
+        np.array([len(cams), W, H], np.int32).tofile(f)
+        np.array([cams[0].tan_fovx, cams[0].tan_fovy], np.float32).tofile(f)
+        pack_cameras(cams).astype(np.float32).tofile(f)
+    res = subprocess.run([exe, ply, cam_bin], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "bad_rounds=0 state_ok=1" in res.stdout

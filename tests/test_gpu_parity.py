@@ -233,6 +233,9 @@ def test_lean_state_flag_changes_no_output_of_the_pass(oracle):
         assert full["num_rendered"] == lean["num_rendered"] > 0
         for k in ("radii", "depths", "means2D", "conic_opacity", "rgb", "keys", "values", "ranges", "n_contrib",
                   "final_T", "out_color"):
-            assert np.array_equal(full[k], lean[k]), (extra, k)
+            a, b = full[k], lean[k]
+            if k == "depths":  # entries of Gaussians that emit nothing hold the all-ones (NaN) pattern: compare bits
+                a, b = a.view(np.uint32), b.view(np.uint32)
+            assert np.array_equal(a, b), (extra, k)
         vis = full["radii"] > 0
         assert np.abs(full["cov3D"].reshape(-1, 6)[vis]).max() > 0  # the default call does fill it

@@ -98,3 +98,72 @@ def test_u8_frame_delivery():
     got = frames_to_u8(x).cpu().numpy()
     assert np.array_equal(got, np.rint(np.clip(x.cpu().numpy(), 0.0, 1.0) * np.float32(255.0)).astype(np.uint8))
     vr.close()
+
+
+def test_renderer_keep_state_serves_the_inspector_fields():
+    """GSR_FLAG_KEEP_STATE + gsr_renderer_map_geometry_state: the nine fields the reference's Inspector reads
+    (Inspector.cpp:174-188 through GSGaussians::mapGeometryState, GSGaussians.cpp:214-219) out of the renderer's
+    private scratch, bit-identical with a plain gsr_forward of the same view."""
+    import torch
+
+    from gsrast_b200.views import ViewRenderer
+
+    sc = S.make_config_scene("C1", P=50_000)[0]
+    W, H = 800, 448
+    cams = Cm.orbit_cameras(3, W, H)
+    vr = ViewRenderer.from_scene(sc, W, H, keep_state=True)
+    out, nr = vr.render(cams, cams[0].tan_fovx, cams[0].tan_fovy)
+    torch.cuda.synchronize()
+    lanes = vr.num_lanes()
+    for lane in range(lanes):
+        v = max(i for i in range(len(cams)) if i % lanes == lane)  # the last view that ran on this lane
+        g = vr.map_geometry_state(lane)
+        single = run_cuda(sc, cams[v])
+        assert np.array_equal(out[v].cpu().numpy(), single["out_color"])
+        vis = single["radii"] > 0
+        assert np.array_equal(g["internal_radii"].cpu().numpy(), single["radii"])
+        assert np.array_equal(g["tiles_touched"].cpu().numpy().view(np.uint32), single["tiles_touched"])
+        assert np.array_equal(g["point_offsets"].cpu().numpy().view(np.uint32), single["point_offsets"])
+        for k in ("depths", "means2D", "conic_opacity", "cov3D", "rgb"):
+            assert np.array_equal(g[k].cpu().numpy()[vis].view(np.uint32), single[k][vis].view(np.uint32)), k
+        assert np.array_equal(g["clamped"].cpu().numpy()[vis], single["clamped"][vis])
+    vr.close()
+    # the default (lean) renderer renders the same frames
+    vr2 = ViewRenderer.from_scene(sc, W, H)
+    out2, nr2 = vr2.render(cams, cams[0].tan_fovx, cams[0].tan_fovy)
+    torch.cuda.synchronize()
+    assert nr2 == nr and torch.equal(out2, out)
+    vr2.close()
+
+
+def test_same_views_on_two_gpus_are_bit_equal():
+    """Multi-GPU correctness of the view sharding: the same four views rendered on cuda:0 and on cuda:1
+    (scene replicated, no torch.cuda.set_device by the caller) must be the same bits.  Needs >= 2 visible devices."""
+    import torch
+
+    from gsrast_b200.views import ViewRenderer
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    sc = S.make_config_scene("C2", P=400_000)[0]
+    W, H = 1280, 720
+    cams = Cm.orbit_cameras(4, W, H)
+    frames, counts = [], []
+    for d in (0, 1):
+        vr = ViewRenderer.from_scene(sc, W, H, device="cuda:%d" % d)
+        out, nr = vr.render(cams, cams[0].tan_fovx, cams[0].tan_fovy)
+        torch.cuda.synchronize(d)
+        host, nr_h = vr.render_host(cams, cams[0].tan_fovx, cams[0].tan_fovy)
+        assert out.device.index == d and nr == nr_h
+        assert np.array_equal(out.cpu().numpy(), host.numpy())
+        frames.append(out.cpu().numpy())
+        counts.append(nr)
+        vr.close()
+    assert counts[0] == counts[1]
+    assert np.array_equal(frames[0], frames[1])
+    # and the single-call path with explicit device tensors, current device left at 0
+    a = run_cuda(sc, cams[0], device="cuda:0")
+    b = run_cuda(sc, cams[0], device="cuda:1")
+    assert a["num_rendered"] == b["num_rendered"] == counts[0][0]
+    assert np.array_equal(a["keys"], b["keys"]) and np.array_equal(a["values"], b["values"])
+    assert np.array_equal(a["out_color"], b["out_color"]) and np.array_equal(a["out_color"], frames[0][0])

@@ -19,6 +19,7 @@ FLAG_LEAN_STATE = 0x8
 FLAG_RADIX_BINNING = 0x4
 FLAG_BLEND_COUNT = 0x10
 FLAG_KEEP_STATE = 0x20
+FLAG_BLEND_ONE_PIXEL = 0x40
 BLEND_COUNTERS = ("tile_rounds", "warp_rounds", "candidates_listed", "warp_trips", "pairs_live", "pairs_passed",
                   "pairs_blended", "splats_staged")
 

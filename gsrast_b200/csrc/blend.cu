@@ -393,6 +393,257 @@ __global__ void __launch_bounds__(BLEND_THREADS, GSR_BLEND_MINB) blend_culled_ke
     }
 }
 
+// -------------------------------------------------------------------------------------------
+// blend_pair_kernel: two pixels per thread on the packed FP32 pipe (FADD2 / FMUL2 / FFMA2 of sm_100, one issue slot
+// for both pixels; a scalar operand is broadcast by the instruction's .F32 operand form, so per-splat coefficients
+// need no duplication — tools/microbench_f32x2.cu measures the issue cost).  One CTA of 128 threads per 16x16 tile,
+// warp w owns the 8x8 quadrant (w&1, w>>1), lane -> (lane&7, lane>>3) and (lane&7, (lane>>3)+4): the two pixels share
+// dx, dx*dx and every per-splat load, and the per-pixel arithmetic of the exponent, alpha, the transmittance test and
+// the colour accumulation is issued once for the pair.  A candidate trip costs ~38 issue slots for 64 pixels where the
+// one-pixel kernel pays 28 for 32; the lists of an 8x8 quadrant are 0.61x as long as those of its two 8x4 halves
+// together (tests/analysis/blend_cull_model.py), list building is done by 4 warps instead of 8, and all 128 threads
+// stage (no idle staging warps).  Arithmetic per pixel is the one-pixel kernel's, operation for operation.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+    u64 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+constexpr int PAIR_THREADS = 128;
+constexpr int PAIR_WARPS = PAIR_THREADS / 32;
+static_assert(CBATCH == PAIR_THREADS, "every thread of the pair kernel stages one splat per round");
+#ifndef GSR_PAIR_MINB
+#define GSR_PAIR_MINB 10   // CTAs of 128 threads per SM: 51 registers
+#endif
+template <bool COUNT>
+__global__ void __launch_bounds__(PAIR_THREADS, GSR_PAIR_MINB) blend_pair_kernel(const BlendParams p) {
+    __shared__ float4 s_splat[CBATCH * 3];
+    __shared__ unsigned char s_mask[CBATCH];                  // bit w: splat can reach warp w's 8x8 quadrant
+    __shared__ unsigned short s_list[PAIR_WARPS][CBATCH];     // per warp: shared-window addresses of its candidates' records
+
+    const int tile = (int)blockIdx.x;
+    const int tile_x = tile % p.grid_x, tile_y = tile / p.grid_x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lx = ((warp & 1) << 3) | (lane & 7), ly = ((warp >> 1) << 3) | (lane >> 3);
+    const int pix_x = tile_x * TILE_X + lx, pix_y0 = tile_y * TILE_Y + ly, pix_y1 = pix_y0 + 4;
+    const bool inside0 = pix_x < p.W && pix_y0 < p.H, inside1 = pix_x < p.W && pix_y1 < p.H;
+    const float tile_x0 = (float)(tile_x * TILE_X), tile_y0 = (float)(tile_y * TILE_Y);
+    const uint32_t lane_lt = (1u << lane) - 1u;
+    unsigned short* my_list = s_list[warp];
+    uint32_t splat_base = (uint32_t)__cvta_generic_to_shared(s_splat);
+    uint32_t list_base = (uint32_t)__cvta_generic_to_shared(my_list);
+    float t_min = p.t_min;
+    float pixf_x = (float)pix_x;
+    u64 npy2 = pk2(-(float)pix_y0, -(float)pix_y1);
+    asm volatile("" : "+r"(splat_base), "+r"(list_base), "+f"(t_min), "+f"(pixf_x), "+l"(npy2));
+    if ((splat_base + (uint32_t)(CBATCH * 48)) >> 16) __trap();  // the lists hold 16-bit shared-window addresses
+    const uint32_t rec_bias = splat_base;
+
+    gsr_pdl_wait();
+    const uint2 range = reinterpret_cast<const uint2*>(p.ranges)[tile];
+    const int total = (int)(range.y - range.x);
+    const int rounds = (total + CBATCH - 1) / CBATCH;
+
+    // pixels outside the image start "terminated" (negative T, see blend_culled_kernel)
+    float T0 = inside0 ? 1.0f : -1.0f, T1 = inside1 ? 1.0f : -1.0f;
+    u64 C0 = 0ull, C1 = 0ull, C2 = 0ull;  // {pixel 0, pixel 1} per channel
+    uint32_t last0 = 0, last1 = 0;
+    bool warp_done = __all_sync(0xffffffffu, !inside0 && !inside1);
+
+    float2 n_xy = make_float2(0.f, 0.f);
+    float4 n_co = make_float4(0.f, 0.f, 0.f, 0.f);
+    float n_c0 = 0.f, n_c1 = 0.f, n_c2 = 0.f;
+    if (tid < total) {
+        const uint32_t id = __ldg(p.point_list + range.x + tid);
+        n_xy = __ldg(reinterpret_cast<const float2*>(p.means2D) + id);
+        n_co = __ldg(reinterpret_cast<const float4*>(p.conic_opacity) + id);
+        const float* col = p.colors + (size_t)id * 3;
+        n_c0 = __ldg(col); n_c1 = __ldg(col + 1); n_c2 = __ldg(col + 2);
+    }
+
+    for (int r = 0; r < rounds; ++r) {
+        if (__syncthreads_and(warp_done)) break;
+        if (COUNT && tid == 0) {
+            atomicAdd(p.counters + 0, 1ull);
+            atomicAdd(p.counters + 7, (unsigned long long)min(CBATCH, total - r * CBATCH));
+        }
+        const int progress = r * CBATCH + tid;
+        uint32_t m = 0;
+        const float2 xy = n_xy;
+        const float4 co = n_co;
+        const float cr = n_c0, cg = n_c1, cb = n_c2;
+        if (progress + CBATCH < total) {
+            const uint32_t id = __ldg(p.point_list + range.x + progress + CBATCH);
+            n_xy = __ldg(reinterpret_cast<const float2*>(p.means2D) + id);
+            n_co = __ldg(reinterpret_cast<const float4*>(p.conic_opacity) + id);
+            const float* col = p.colors + (size_t)id * 3;
+            n_c0 = __ldg(col); n_c1 = __ldg(col + 1); n_c2 = __ldg(col + 2);
+        }
+        if (progress < total) {
+            const float a = co.x, b = co.y, c = co.z, o = co.w;
+            s_splat[3 * tid + 0] = make_float4(xy.x, xy.y, -0.5f * LOG2E * a, -LOG2E * b);
+            s_splat[3 * tid + 1] = make_float4(-0.5f * LOG2E * c, o, cr, cg);
+            s_splat[3 * tid + 2] = make_float4(cb, 0.f, 0.f, 0.f);
+            // which 8x8 quadrants can see this splat with alpha >= 1/255 (same bounds as blend_culled_kernel)
+            const float det = a * c - b * b;
+            if (!(o >= ALPHA_MIN * 0.999f)) {
+                m = 0;
+            } else if (!(a > 0.f && c > 0.f && det > 0.f) || !(fabsf(xy.x) < 1e7f) || !(fabsf(xy.y) < 1e7f)) {
+                m = 0xfu;
+            } else {
+                const float thr = -__logf(255.0f * o) * 1.0001f - 1e-3f;
+                const float sc = __fdividef(-2.0f * thr, det);
+                const float ex = cull_sqrt(sc * c) * 1.0001f + 0.01f, ey = cull_sqrt(sc * a) * 1.0001f + 0.01f;
+                const float bx1 = xy.x - tile_x0, by1 = xy.y - tile_y0;
+                const float xlo = bx1 - ex, xhi = bx1 + ex, ylo = by1 - ey, yhi = by1 + ey;
+                if (!(ex < 1e7f) || !(ey < 1e7f)) {
+                    m = 0xfu;
+                } else {
+                    const uint32_t colm = ((xlo <= 7.f && xhi >= 0.f) ? 1u : 0u) | ((xlo <= 15.f && xhi >= 8.f) ? 2u : 0u);
+                    uint32_t cand = ((ylo <= 7.f && yhi >= 0.f) ? colm : 0u) | ((ylo <= 15.f && yhi >= 8.f) ? (colm << 2) : 0u);
+                    if (cand) {
+                        const float mba = cull_div(-b, a), mbc = cull_div(-b, c);
+                        while (cand) {
+                            const int w = __ffs(cand) - 1;
+                            cand &= cand - 1;
+                            const float wx1 = bx1 - (float)((w & 1) << 3), wy1 = by1 - (float)((w >> 1) << 3);
+                            if (max_power_in_box(a, b, c, mba, mbc, wx1 - 7.f, wx1, wy1 - 7.f, wy1) >= thr) m |= 1u << w;
+                        }
+                    }
+                }
+            }
+        }
+        s_mask[tid] = (unsigned char)m;
+        __syncthreads();
+
+        if (!warp_done) {
+            int n = 0;
+#pragma unroll
+            for (int c0 = 0; c0 < CBATCH; c0 += 32) {
+                const bool mine = (s_mask[c0 + lane] >> warp) & 1u;
+                const unsigned bits = __ballot_sync(0xffffffffu, mine);
+                if (mine) my_list[n + __popc(bits & lane_lt)] = (unsigned short)(rec_bias + (uint32_t)((c0 + lane) * 48));
+                n += __popc(bits);
+            }
+            __syncwarp();
+            if (COUNT && lane == 0) { atomicAdd(p.counters + 1, 1ull); atomicAdd(p.counters + 2, (unsigned long long)n); }
+            uint32_t c_trips = 0, c_live = 0, c_cand = 0, c_blend = 0;
+            uint32_t last_off0 = 0xffffffffu, last_off1 = 0xffffffffu;
+            for (int i0 = 0; i0 < n; i0 += 16) {
+                const int i1 = min(n, i0 + 16);
+#pragma unroll 2
+                for (int i = i0; i < i1; ++i) {
+                    const uint32_t rec = lds16(list_base + 2u * (uint32_t)i);
+                    const float4 a = lds128(rec);        // x, y, a', b'
+                    const float4 b = lds128(rec + 16u);  // c', o, r, g
+                    const float cb3 = lds32(rec + 32u);
+                    const float dx = a.x - pixf_x;
+                    const u64 dy2 = add2(pk2(a.y, a.y), npy2);
+                    const float dxdx = dx * dx;
+                    // per pixel exactly blend_culled_kernel's fma(a', dx*dx, fma(c', dy*dy, b'*(dx*dy)))
+                    const u64 bd2 = mul2(pk2(a.w, a.w), mul2(pk2(dx, dx), dy2));
+                    const u64 u2 = fma2(pk2(b.x, b.x), mul2(dy2, dy2), bd2);
+                    const u64 pw2 = fma2(pk2(a.z, a.z), pk2(dxdx, dxdx), u2);
+                    float p0, p1;
+                    unpk2(pw2, p0, p1);
+                    const u64 al2 = mul2(pk2(b.y, b.y), pk2(ex2_approx(p0), ex2_approx(p1)));
+                    float al0, al1;
+                    unpk2(al2, al0, al1);
+                    al0 = fminf(0.99f, al0);
+                    al1 = fminf(0.99f, al1);
+                    const u64 T2 = pk2(T0, T1);
+                    const u64 w2 = mul2(pk2(al0, al1), T2);
+                    const u64 tt2 = sub2(T2, w2);  // T*(1-alpha) as T - alpha*T
+                    float w0, w1, tt0, tt1;
+                    unpk2(w2, w0, w1);
+                    unpk2(tt2, tt0, tt1);
+                    const bool cand0 = (p0 <= 0.0f) && (al0 >= ALPHA_MIN), cand1 = (p1 <= 0.0f) && (al1 >= ALPHA_MIN);
+                    const bool pass0 = tt0 >= t_min, pass1 = tt1 >= t_min;
+                    const bool ok0 = cand0 && pass0, ok1 = cand1 && pass1;
+                    if (COUNT) {
+                        ++c_trips;
+                        c_live += (T0 > 0.0f) + (T1 > 0.0f);
+                        c_cand += (cand0 && T0 > 0.0f) + (cand1 && T1 > 0.0f);
+                        c_blend += ok0 + ok1;
+                    }
+                    if (ok0) last_off0 = rec;
+                    if (ok1) last_off1 = rec;
+                    // a pixel that does not blend this splat adds +0 * colour (its weight is selected to zero)
+                    const u64 wm2 = pk2(ok0 ? w0 : 0.0f, ok1 ? w1 : 0.0f);
+                    C0 = fma2(pk2(b.z, b.z), wm2, C0);
+                    C1 = fma2(pk2(b.w, b.w), wm2, C1);
+                    C2 = fma2(pk2(cb3, cb3), wm2, C2);
+                    if (cand0) T0 = pass0 ? tt0 : -fabsf(T0);
+                    if (cand1) T1 = pass1 ? tt1 : -fabsf(T1);
+                }
+                if (__all_sync(0xffffffffu, T0 <= 0.0f && T1 <= 0.0f)) {
+                    warp_done = true;
+                    break;
+                }
+            }
+            if (last_off0 != 0xffffffffu) last0 = (uint32_t)(r * CBATCH + 1) + (last_off0 - rec_bias) / 48u;
+            if (last_off1 != 0xffffffffu) last1 = (uint32_t)(r * CBATCH + 1) + (last_off1 - rec_bias) / 48u;
+            if (COUNT) {
+                c_live = __reduce_add_sync(0xffffffffu, c_live);
+                c_cand = __reduce_add_sync(0xffffffffu, c_cand);
+                c_blend = __reduce_add_sync(0xffffffffu, c_blend);
+                if (lane == 0) {
+                    atomicAdd(p.counters + 3, (unsigned long long)c_trips * 2ull);  // in 32-pixel units, like the one-pixel kernel
+                    atomicAdd(p.counters + 4, (unsigned long long)c_live);
+                    atomicAdd(p.counters + 5, (unsigned long long)c_cand);
+                    atomicAdd(p.counters + 6, (unsigned long long)c_blend);
+                }
+            }
+        }
+    }
+    T0 = fabsf(T0);
+    T1 = fabsf(T1);
+    float c00, c01, c10, c11, c20, c21;
+    unpk2(C0, c00, c01);
+    unpk2(C1, c10, c11);
+    unpk2(C2, c20, c21);
+    const size_t plane = (size_t)p.W * p.H;
+    const float bg0 = __ldg(p.background + 0), bg1 = __ldg(p.background + 1), bg2 = __ldg(p.background + 2);
+    if (inside0) {
+        const size_t pix = (size_t)pix_y0 * p.W + pix_x;
+        p.final_T[pix] = T0;
+        p.n_contrib[pix] = last0;
+        p.out_color[pix] = fmaf(T0, bg0, c00);
+        p.out_color[pix + plane] = fmaf(T0, bg1, c10);
+        p.out_color[pix + 2 * plane] = fmaf(T0, bg2, c20);
+    }
+    if (inside1) {
+        const size_t pix = (size_t)pix_y1 * p.W + pix_x;
+        p.final_T[pix] = T1;
+        p.n_contrib[pix] = last1;
+        p.out_color[pix] = fmaf(T1, bg0, c01);
+        p.out_color[pix + plane] = fmaf(T1, bg1, c11);
+        p.out_color[pix + 2 * plane] = fmaf(T1, bg2, c21);
+    }
+}
+
 __global__ void fill_background_kernel(int n, const float* __restrict__ background, float* __restrict__ out_color,
                                        float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -406,13 +657,37 @@ __global__ void fill_background_kernel(int n, const float* __restrict__ backgrou
 
 }  // namespace
 
-int launch_blend(const BlendParams& p, bool simple, cudaStream_t s) {
+// Which blend kernel is the default: GSR_BLEND_PAIR (compile time), overridden by the environment variable
+// GSR_BLEND_PAIR=0/1 (A/B runs on one build).
+#ifndef GSR_BLEND_PAIR
+#define GSR_BLEND_PAIR 1
+#endif
+#ifndef GSR_PAIR_CARVEOUT
+#define GSR_PAIR_CARVEOUT 44   // ten 7.3 KB CTAs (+1 KB reserved each) need > 64 KB of shared memory
+#endif
+static bool blend_use_pair() {
+    static const int v = [] {
+        const char* e = getenv("GSR_BLEND_PAIR");
+        return e ? atoi(e) : GSR_BLEND_PAIR;
+    }();
+    return v != 0;
+}
+
+int launch_blend(const BlendParams& p, bool simple, cudaStream_t s, bool one_pixel) {
     const int tiles = p.grid_x * p.grid_y;
     if (tiles <= 0) return 0;
     cudaError_t e;
     if (simple)
         e = launch_pdl(blend_simple_kernel, dim3(tiles), dim3(BLEND_THREADS), 0, s, p);
-    else if (p.counters) {
+    else if (!one_pixel && blend_use_pair()) {
+        if (p.counters) {
+            GSR_CARVEOUT(blend_pair_kernel<true>, "BLEND", GSR_PAIR_CARVEOUT);
+            e = launch_pdl(blend_pair_kernel<true>, dim3(tiles), dim3(PAIR_THREADS), 0, s, p);
+        } else {
+            GSR_CARVEOUT(blend_pair_kernel<false>, "BLEND", GSR_PAIR_CARVEOUT);
+            e = launch_pdl(blend_pair_kernel<false>, dim3(tiles), dim3(PAIR_THREADS), 0, s, p);
+        }
+    } else if (p.counters) {
         GSR_CARVEOUT(blend_culled_kernel<true>, "BLEND", GSR_BLEND_CARVEOUT);
         e = launch_pdl(blend_culled_kernel<true>, dim3(tiles), dim3(BLEND_THREADS), 0, s, p);
     } else {

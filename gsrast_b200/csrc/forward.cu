@@ -467,7 +467,7 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         GSR_CUDA_TRY(cudaMemsetAsync(img.blend_counters, 0, GSR_BLEND_COUNTERS * sizeof(unsigned long long), s));
         bp.counters = img.blend_counters;
     }
-    GSR_STAGE(launch_blend(bp, (a->flags & GSR_FLAG_BLEND_SIMPLE) != 0, s));
+    GSR_STAGE(launch_blend(bp, (a->flags & GSR_FLAG_BLEND_SIMPLE) != 0, s, (a->flags & GSR_FLAG_BLEND_ONE_PIXEL) != 0));
     tm.mark();  // 7
 
     if (a->timings) {

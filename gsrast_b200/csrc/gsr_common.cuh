@@ -190,7 +190,9 @@ struct BlendParams {
     const uint32_t* tile_order;  // optional
     unsigned long long* counters;  // optional [GSR_BLEND_COUNTERS]: run the counting instantiation (GSR_FLAG_BLEND_COUNT)
 };
-int launch_blend(const BlendParams& p, bool simple, cudaStream_t s);
+// simple: the reference-structured kernel; one_pixel: blend_culled_kernel (one pixel per thread) instead of the default
+// blend_pair_kernel (two pixels per thread on the packed FP32 pipe)
+int launch_blend(const BlendParams& p, bool simple, cudaStream_t s, bool one_pixel = false);
 int launch_fill_background(int W, int H, const float* background, float* out_color, float* final_T,
                            uint32_t* n_contrib, cudaStream_t s);
 

@@ -111,6 +111,19 @@ __global__ void __launch_bounds__(PRE_THREADS, GSR_PRE_MINB) preprocess_kernel(c
         }
     }
     const bool need_scales = (p.cov3D_precomp == nullptr);
+    // The rotation and the opacity of every Gaussian are requested HERE, with the mean / scale streams, although they
+    // are only used by Gaussians that survive the frustum test (rotation) or emit pairs (opacity): issued behind those
+    // tests they were two more dependent DRAM round trips per CTA (ncu: 55 % long-scoreboard stalls); up front the
+    // four coalesced streams fly together, at the price of 20 B of reads per culled Gaussian.
+#ifndef GSR_PRE_HOIST
+#define GSR_PRE_HOIST 1
+#endif
+    float4 q_early = make_float4(0.f, 0.f, 0.f, 0.f);
+    float opac_early = 0.f;
+    if (GSR_PRE_HOIST && valid) {
+        if (need_scales) q_early = ldg_f4(p.rotations + (size_t)idx * 4);
+        opac_early = __ldg(p.opacities + idx);
+    }
     if (need_scales && p.scales_stride == 3) {
         const float* g = p.scales + (size_t)base * 3;
         const int nf = nvalid * 3;
@@ -186,14 +199,15 @@ __global__ void __launch_bounds__(PRE_THREADS, GSR_PRE_MINB) preprocess_kernel(c
         // the covariance math and the warp compaction): start pulling it into L2.  Only for centres on the screen
         // (GSR_PRE_PREFETCH_BOUND in NDC; a hint: an off-screen centre whose radius reaches the screen just misses) —
         // at 1.25 the Gaussians of the band around the screen, which are culled a moment later, cost ~35 MB of SH reads
-        // per C2 frame.  GSR_PRE_PREFETCH_MODE 1: only the 128-byte line the 192-byte block owns entirely (the other
-        // 64 bytes share their line with a neighbour that may be culled; they arrive with the demand loads);
-        // 0: both lines; 2: no prefetch.
+        // per C2 frame (preprocess 0.170 -> 0.167 ms at 1.03, profiles/r02_ab.txt).  GSR_PRE_PREFETCH_MODE 0: both
+        // 128-byte lines the 192-byte block touches; 1: only the line it owns entirely (the other 64 bytes share
+        // their line with a neighbour that may be culled) — measured SLOWER, 0.177 ms: the demand loads of the
+        // un-prefetched third then wait on DRAM; 2: no prefetch.
 #ifndef GSR_PRE_PREFETCH_BOUND
 #define GSR_PRE_PREFETCH_BOUND 1.03f
 #endif
 #ifndef GSR_PRE_PREFETCH_MODE
-#define GSR_PRE_PREFETCH_MODE 1
+#define GSR_PRE_PREFETCH_MODE 0
 #endif
         if (!COMPAT && GSR_PRE_PREFETCH_MODE != 2 && alive && p.colors_precomp == nullptr &&
             fabsf(prx) < GSR_PRE_PREFETCH_BOUND && fabsf(pry) < GSR_PRE_PREFETCH_BOUND) {
@@ -230,7 +244,7 @@ __global__ void __launch_bounds__(PRE_THREADS, GSR_PRE_MINB) preprocess_kernel(c
                     float4 s4 = ldg_f4(p.scales + (size_t)idx * 4);
                     sx = s4.x; sy = s4.y; sz = s4.z;
                 }
-                const float4 q = ldg_f4(p.rotations + (size_t)idx * 4);
+                const float4 q = GSR_PRE_HOIST ? q_early : ldg_f4(p.rotations + (size_t)idx * 4);
                 const float s0 = fmul(p.scale_modifier, sx), s1 = fmul(p.scale_modifier, sy),
                             s2 = fmul(p.scale_modifier, sz);
                 if (!COMPAT) {
@@ -359,7 +373,7 @@ __global__ void __launch_bounds__(PRE_THREADS, GSR_PRE_MINB) preprocess_kernel(c
                 radius_out = ri;
                 o_depth = depth;
                 o_xy = make_float2(ix, iy);
-                o_conic = make_float4(conx, cony, conz, __ldg(p.opacities + idx));
+                o_conic = make_float4(conx, cony, conz, GSR_PRE_HOIST ? opac_early : __ldg(p.opacities + idx));
                 if (p.colors_precomp == nullptr) {
                     if (!COMPAT) {
                         need_sh = true;
@@ -443,24 +457,47 @@ __global__ void __launch_bounds__(PRE_THREADS, GSR_PRE_MINB) preprocess_kernel(c
             const int n = __popc(mask);
             const int q = lane & 3;
             const int nk = max(0, min(4, ncoef - 4 * q));  // coefficients this lane owns: 4q .. 4q+nk-1
+            // Software pipeline (GSR_PRE_SH_PIPE): the 48 bytes of the NEXT group of 8 survivors are requested before the
+            // current group is evaluated, so a warp with 3-4 groups pays one exposed L2 round trip instead of one each.
+#ifndef GSR_PRE_SH_PIPE
+#define GSR_PRE_SH_PIPE 1
+#endif
+            float sn[12];
+            int gnext = 0;
+            auto fetch = [&](int slot_, float* dst, int& g_) {
+                g_ = 0;
+#pragma unroll
+                for (int i = 0; i < 12; ++i) dst[i] = 0.f;
+                if (slot_ < n) {
+                    g_ = s_queue[warp][slot_];
+                    const float* sp = p.shs + ((size_t)g_ * p.M + 4 * q) * 3;
+                    if (nk == 4 && vec_sh) {
+                        const float4 a = ldg_f4(sp), b = ldg_f4(sp + 4), cc = ldg_f4(sp + 8);
+                        dst[0] = a.x; dst[1] = a.y; dst[2] = a.z; dst[3] = a.w;
+                        dst[4] = b.x; dst[5] = b.y; dst[6] = b.z; dst[7] = b.w;
+                        dst[8] = cc.x; dst[9] = cc.y; dst[10] = cc.z; dst[11] = cc.w;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 12; ++i) dst[i] = (i < nk * 3) ? __ldg(sp + i) : 0.f;
+                    }
+                }
+            };
+            if (GSR_PRE_SH_PIPE) fetch(lane >> 2, sn, gnext);
             for (int r0 = 0; r0 < n; r0 += 8) {
                 const int slot = r0 + (lane >> 2);
                 const bool act = slot < n;
                 float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
-                int gidx = 0;
-                if (act) {
-                    gidx = s_queue[warp][slot];
-                    float s[12];
-                    const float* sp = p.shs + ((size_t)gidx * p.M + 4 * q) * 3;
-                    if (nk == 4 && vec_sh) {
-                        float4 a = ldg_f4(sp), b = ldg_f4(sp + 4), cc = ldg_f4(sp + 8);
-                        s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w;
-                        s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
-                        s[8] = cc.x; s[9] = cc.y; s[10] = cc.z; s[11] = cc.w;
-                    } else {
+                float s[12];
+                int gidx;
+                if (GSR_PRE_SH_PIPE) {
 #pragma unroll
-                        for (int i = 0; i < 12; ++i) s[i] = (i < nk * 3) ? __ldg(sp + i) : 0.f;
-                    }
+                    for (int i = 0; i < 12; ++i) s[i] = sn[i];
+                    gidx = gnext;
+                    if (r0 + 8 < n) fetch(slot + 8, sn, gnext);  // warp-uniform branch
+                } else {
+                    fetch(slot, s, gidx);
+                }
+                if (act) {
                     const float4 bq = bp[slot * 4 + (q ^ ((slot >> 1) & 3))];
                     acc0 = __fmaf_rn(bq.w, s[9], __fmaf_rn(bq.z, s[6], __fmaf_rn(bq.y, s[3], fmul(bq.x, s[0]))));
                     acc1 = __fmaf_rn(bq.w, s[10], __fmaf_rn(bq.z, s[7], __fmaf_rn(bq.y, s[4], fmul(bq.x, s[1]))));

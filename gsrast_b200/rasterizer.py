@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import FLAG_BLEND_COUNT, FLAG_BLEND_SIMPLE, FLAG_GSRAST_COMPAT  # noqa: F401
+from ._lib import FLAG_BLEND_COUNT, FLAG_BLEND_ONE_PIXEL, FLAG_BLEND_SIMPLE, FLAG_GSRAST_COMPAT  # noqa: F401
 
 NUM_CHANNELS = 3  # Config.hpp:46
 BLOCK_X = 16      # Config.hpp:47

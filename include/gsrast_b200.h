@@ -49,6 +49,8 @@ typedef char* (*gsr_alloc_fn)(size_t bytes, void* user);
 #define GSR_FLAG_BLEND_COUNT 0x10u  /* with `timings`: run the counting instantiation of the blend kernel (same arithmetic)
                                        and return its work counters in gsr_stage_times.blend_counters — the unit
                                        SURVEY 8(d) rates the blend in.  Slower; for reporting, never on a timed path */
+#define GSR_FLAG_BLEND_ONE_PIXEL 0x40u /* use the one-pixel-per-thread culled blend kernel instead of the default
+                                          two-pixels-per-thread kernel on the packed FP32 pipe; for A/B tests */
 #define GSR_FLAG_KEEP_STATE 0x20u   /* gsr_renderer_create only: keep every geometry-state field materialised (no
                                        GSR_FLAG_LEAN_STATE) so gsr_renderer_map_geometry_state serves the reference's
                                        Inspector panel (apps/gsrast/Inspector.cpp:174-188) */

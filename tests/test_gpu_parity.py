@@ -83,6 +83,26 @@ def test_blend_kernels_agree(oracle):
     assert psnr(a["out_color"], b["out_color"]) >= 50.0
 
 
+@pytest.mark.parametrize("cfg,P,W,H,compat", [("C2", 150_000, 1000, 555, False), ("C5", 60_000, 960, 540, False),
+                                               ("C1", 60_000, 650, 366, True)])
+def test_one_pixel_and_pair_blend_kernels_agree(oracle, cfg, P, W, H, compat):
+    """Default = two pixels per thread on the packed FP32 pipe (blend_pair_kernel); GSR_FLAG_BLEND_ONE_PIXEL = the
+    one-pixel culled kernel.  Per pixel the arithmetic is the same operation for operation, so the frames, final_T
+    and n_contrib must be IDENTICAL; both are held to the oracle (ragged sizes: half tile rows / columns)."""
+    from gsrast_b200.rasterizer import FLAG_BLEND_ONE_PIXEL
+
+    sc = _scene(cfg, P)
+    cam = Cm.orbit_cameras(5, W, H)[2]
+    a = run_cuda(sc, cam, compat=compat, background=(0.2, 0.1, 0.4))
+    b = run_cuda(sc, cam, compat=compat, background=(0.2, 0.1, 0.4), flags=FLAG_BLEND_ONE_PIXEL)
+    assert a["num_rendered"] == b["num_rendered"] > 0
+    assert np.array_equal(a["out_color"], b["out_color"])
+    assert np.array_equal(a["final_T"], b["final_T"]) and np.array_equal(a["n_contrib"], b["n_contrib"])
+    ref = run_oracle(oracle, sc, cam, compat=compat, background=(0.2, 0.1, 0.4))
+    cmax = float(np.abs(ref.rgb[ref.radii > 0]).max()) if compat else 1.0
+    assert_parity(a, ref, colours_from_sh=sc.colors_precomp is None, colour_max=cmax)
+
+
 def test_ragged_resolution_and_orbit_camera(oracle):
     """Width/height not multiples of 16 (1080p-like half tile row) and an off-axis camera."""
     sc = _scene("C2", 80_000)

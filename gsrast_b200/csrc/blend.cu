@@ -435,7 +435,8 @@ constexpr int PAIR_THREADS = 128;
 constexpr int PAIR_WARPS = PAIR_THREADS / 32;
 static_assert(CBATCH == PAIR_THREADS, "every thread of the pair kernel stages one splat per round");
 #ifndef GSR_PAIR_MINB
-#define GSR_PAIR_MINB 10   // CTAs of 128 threads per SM: 51 registers
+#define GSR_PAIR_MINB 8    // CTAs of 128 threads per SM (64 registers, no spills); measured C2 / C5 blend: 12 CTAs 0.290 /
+                           // 1.173 ms, 10 CTAs 0.272 / 1.097, 8 CTAs 0.265 / 1.075 (profiles/r02b_ab_*.txt)
 #endif
 template <bool COUNT>
 __global__ void __launch_bounds__(PAIR_THREADS, GSR_PAIR_MINB) blend_pair_kernel(const BlendParams p) {
@@ -579,6 +580,9 @@ __global__ void __launch_bounds__(PAIR_THREADS, GSR_PAIR_MINB) blend_pair_kernel
                     float w0, w1, tt0, tt1;
                     unpk2(w2, w0, w1);
                     unpk2(tt2, tt0, tt1);
+                    // The decision tail of a pixel: 4 FSETP + 2 FSEL + 1 SEL on the ALU pipe (the busiest pipe of this
+                    // kernel).  An inline-PTX form with a two-destination setp (ok | stop from one compare) and
+                    // predicated moves was tried: ptxas turns it back into FSETP + PLOP3 + four selects — dropped.
                     const bool cand0 = (p0 <= 0.0f) && (al0 >= ALPHA_MIN), cand1 = (p1 <= 0.0f) && (al1 >= ALPHA_MIN);
                     const bool pass0 = tt0 >= t_min, pass1 = tt1 >= t_min;
                     const bool ok0 = cand0 && pass0, ok1 = cand1 && pass1;
@@ -591,12 +595,13 @@ __global__ void __launch_bounds__(PAIR_THREADS, GSR_PAIR_MINB) blend_pair_kernel
                     if (ok0) last_off0 = rec;
                     if (ok1) last_off1 = rec;
                     // a pixel that does not blend this splat adds +0 * colour (its weight is selected to zero)
-                    const u64 wm2 = pk2(ok0 ? w0 : 0.0f, ok1 ? w1 : 0.0f);
+                    const float wm0 = ok0 ? w0 : 0.0f, wm1 = ok1 ? w1 : 0.0f;
+                    if (cand0) T0 = pass0 ? tt0 : -fabsf(T0);
+                    if (cand1) T1 = pass1 ? tt1 : -fabsf(T1);
+                    const u64 wm2 = pk2(wm0, wm1);
                     C0 = fma2(pk2(b.z, b.z), wm2, C0);
                     C1 = fma2(pk2(b.w, b.w), wm2, C1);
                     C2 = fma2(pk2(cb3, cb3), wm2, C2);
-                    if (cand0) T0 = pass0 ? tt0 : -fabsf(T0);
-                    if (cand1) T1 = pass1 ? tt1 : -fabsf(T1);
                 }
                 if (__all_sync(0xffffffffu, T0 <= 0.0f && T1 <= 0.0f)) {
                     warp_done = true;

@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(PRE_THREADS, GSR_PRE_MINB) preprocess_kernel(c
             // Software pipeline (GSR_PRE_SH_PIPE): the 48 bytes of the NEXT group of 8 survivors are requested before the
             // current group is evaluated, so a warp with 3-4 groups pays one exposed L2 round trip instead of one each.
 #ifndef GSR_PRE_SH_PIPE
-#define GSR_PRE_SH_PIPE 1
+#define GSR_PRE_SH_PIPE 0
 #endif
             float sn[12];
             int gnext = 0;

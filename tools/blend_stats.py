@@ -1,29 +1,29 @@
 #!/usr/bin/env python
-"""blend_stats.py [workload] — diagnostics: how many 256-splat batches the blend stages per tile versus how many the
-deepest contributing splat of the tile needed.  Needs a library built with -DGSR_BLEND_STATS
-(tools/build_variant.sh stats -DGSR_BLEND_STATS; GSRAST_B200_LIB=gsrast_b200/variants/lib_stats.so)."""
-import ctypes as C, sys, os
+"""blend_stats.py [workload] — the blend's work counters for one frame (GSR_FLAG_BLEND_COUNT: the counting instantiation
+of the default kernel; include/gsrast_b200.h gsr_stage_times.blend_counters), for the one-pixel and the two-pixel kernel."""
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 from gsrast_b200 import _lib, camera, scene
-from gsrast_b200.views import ViewRenderer
+from gsrast_b200 import rasterizer as Rz
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "C2"
 sc, cfg = scene.make_config_scene(wl)
 W, H = cfg["W"], cfg["H"]
-vr = ViewRenderer.from_scene(sc, W, H, device=torch.device("cuda", 0))
 cam = camera.default_camera(W, H)
-packed = np.stack([cam.packed()]).astype(np.float32)
-out = torch.empty((1, 3, H, W), dtype=torch.float32, device="cuda")
-L = _lib.lib()
-st = (C.c_ulonglong * 4)()
-vr.render(packed, cam.tan_fovx, cam.tan_fovy, out=out)
-L.gsr_debug_blend_stats(st, 1)
-_, nr = vr.render(packed, cam.tan_fovx, cam.tan_fovy, out=out)
-L.gsr_debug_blend_stats(st, 1)
 tiles = ((W + 15) // 16) * ((H + 15) // 16)
-R = nr[0]
-print("%s: R=%d tiles=%d  rounds available %.2f/tile" % (wl, R, tiles, R / 256 / tiles))
-print("tile-rounds staged %d (%.2f/tile)  needed by deepest n_contrib %d (%.2f/tile)" % (st[0], st[0] / tiles, st[3], st[3] / tiles))
-print("warp-rounds walking a list %d (%.2f of 8 per staged round)  candidate trips %d (%.3f per pair)" %
-      (st[1], st[1] / max(st[0], 1), st[2], st[2] / R))
+for name, fl in (("two pixels / thread (default)", 0), ("one pixel / thread", _lib.FLAG_BLEND_ONE_PIXEL)):
+    g = Rz.GSGaussians(W, H, device="cuda", use_rects=False, flags=fl | _lib.FLAG_BLEND_COUNT)
+    g.configure_from_splat_data(sc)
+    g.draw(cam, timings=True)
+    R, tm = g.draw(cam, timings=True)
+    c = tm["blend_counters"]
+    print("%s  %s: R=%d  blend %.3f ms (counting build)" % (wl, name, R, tm["blend_ms"]))
+    print("   rounds staged %.2f/tile of %.2f available; splats staged %d (%.1f %% of R)" %
+          (c["tile_rounds"] / tiles, R / 128 / tiles, c["splats_staged"], 100.0 * c["splats_staged"] / R))
+    print("   warp trips (32-pixel units) %d = %.2f per staged splat; evaluated pairs %d; live %.1f %%, passed %.1f %%, blended %.1f %%" %
+          (c["warp_trips"], c["warp_trips"] / max(c["splats_staged"], 1), 32 * c["warp_trips"],
+           100.0 * c["pairs_live"] / max(32 * c["warp_trips"], 1), 100.0 * c["pairs_passed"] / max(32 * c["warp_trips"], 1),
+           100.0 * c["pairs_blended"] / max(32 * c["warp_trips"], 1)))
+    del g
+    torch.cuda.empty_cache()

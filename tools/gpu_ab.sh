@@ -6,10 +6,14 @@ if [ -z "$NOTEST" ]; then
 timeout 1200 python -m pytest tests -m gpu -q --timeout 900 -x 2>&1 | tail -15 > gpurun_out/pytest_gpu.log
 tail -4 gpurun_out/pytest_gpu.log
 fi
+# ENVS="NAME=VALUE NAME2=VALUE2 ...": additionally run the default library once per entry with that variable set
+for e in $ENVS; do ln -sf $PWD/gsrast_b200/libgsrast_b200.so gsrast_b200/variants/lib_env_${e//[^A-Za-z0-9_]/_}.so; done
 for round in $(seq 1 ${ROUNDS:-2}); do
 for lib in gsrast_b200/variants/lib_*.so; do
   n=$(basename $lib .so)
-  GSRAST_B200_LIB=$PWD/$lib timeout 600 python bench.py --steps ${STEPS:-300} --warmup 10 --no-cpu-baseline --workload ${WL:-C2} > gpurun_out/bench_${n}_$round.log 2>&1
+  envset=""
+  for e in $ENVS; do [ "lib_env_${e//[^A-Za-z0-9_]/_}" = "$n" ] && envset="$e"; done
+  env $envset GSRAST_B200_LIB=$PWD/$lib timeout 600 python bench.py --steps ${STEPS:-300} --warmup 10 --no-cpu-baseline --workload ${WL:-C2} > gpurun_out/bench_${n}_$round.log 2>&1
   python - <<PY
 import json
 try:

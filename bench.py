@@ -174,8 +174,10 @@ def job_cameras(workload, K, Wm, world, rank, W, H):
 
     if workload != "C4":
         return [camera.default_camera(W, H)] * (K + Wm)
-    allc = camera.orbit_cameras((K + Wm) * world, W, H)
-    return [allc[i] for i in shard_views(len(allc), rank, world)]
+    # BASELINE.json configs[3]: a batch of 256 camera poses; job view v uses pose v % 256, so the views do not depend
+    # on --steps (both arms of a driver run see the same poses whatever K each is given)
+    poses = camera.orbit_cameras(256, W, H)
+    return [poses[v % 256] for v in shard_views((K + Wm) * world, rank, world)]
 
 
 def workload_config(workload, sc, W, H, world, R, P_vis, cam_desc):
@@ -188,7 +190,8 @@ def workload_config(workload, sc, W, H, world, R, P_vis, cam_desc):
 
 def camera_desc(workload, world):
     if workload == "C4":
-        return "seeded orbit, view v -> rank v %% %d; num_rendered / visible_gaussians are those of rank 0's first timed view" % world
+        return ("256 seeded orbit poses, job view v -> pose v %% 256 on rank v %% %d; num_rendered / visible_gaussians are "
+                "those of rank 0's first timed view" % world)
     return "viewer's initial pose (0,0,-5) -> origin, fovy 45 deg"
 
 

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(PRE_THREADS) duplicate_sorted_kernel(
     const int P_all, const int grid_x, const uint32_t* __restrict__ sorted_ids, const uint2* __restrict__ sorted_rects,
     const uint32_t* __restrict__ block_offsets, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
     uint32_t* __restrict__ hist, const int tile_bits, const uint32_t* __restrict__ n_sorted, const int coarse,
-    unsigned long long* __restrict__ fuse_state, const int fuse_blocks, uint32_t* error_flag) {
+    unsigned long long* __restrict__ fuse_state, const int fuse_blocks, uint32_t* error_flag, const int presorted) {
     __shared__ uint32_t s_excl[DUP_GAUSS + 1];
     // 16-byte aligned: the compiler reads the 8 warp sums with LDS.128, which otherwise straddles s_excl[DUP_GAUSS]
     // (unused lane of the vector, but compute-sanitizer racecheck rightly flags the overlap with its later store)
@@ -258,7 +258,25 @@ __global__ void __launch_bounds__(PRE_THREADS) duplicate_sorted_kernel(
     uint32_t boff = FUSED ? 0u : __ldg(block_offsets + block);
     uint2 rec[DUP_GPT];
     uint32_t gid[DUP_GPT];
-    if (FUSED) {
+    if (FUSED && presorted) {
+        // the rects arrive in depth order and final units (the last depth pass of the sort wrote them): coalesced loads,
+        // offsets by look-back below — no gather, no separate scan
+        if (i0 + DUP_GPT <= P) {
+            const uint4 r01 = __ldg(reinterpret_cast<const uint4*>(sorted_rects + i0));
+            const uint4 r23 = __ldg(reinterpret_cast<const uint4*>(sorted_rects + i0) + 1);
+            const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(sorted_ids + i0));
+            rec[0] = make_uint2(r01.x, r01.y); rec[1] = make_uint2(r01.z, r01.w);
+            rec[2] = make_uint2(r23.x, r23.y); rec[3] = make_uint2(r23.z, r23.w);
+            gid[0] = g4.x; gid[1] = g4.y; gid[2] = g4.z; gid[3] = g4.w;
+        } else {
+#pragma unroll
+            for (int c = 0; c < DUP_GPT; ++c) {
+                const bool ok = i0 + c < P;
+                rec[c] = ok ? __ldg(sorted_rects + i0 + c) : make_uint2(0u, 0u);
+                gid[c] = ok ? __ldg(sorted_ids + i0 + c) : 0u;
+            }
+        }
+    } else if (FUSED) {
         if (i0 + DUP_GPT <= P) {
             const uint4 g4 = __ldg(reinterpret_cast<const uint4*>(sorted_ids + i0));
             gid[0] = g4.x; gid[1] = g4.y; gid[2] = g4.z; gid[3] = g4.w;
@@ -513,7 +531,7 @@ int launch_duplicate_sorted(int P, int grid_x, const uint32_t* sorted_ids, const
     GSR_CARVEOUT(duplicate_sorted_kernel<false>, "DUP", -1);
     duplicate_sorted_kernel<false><<<blocks, PRE_THREADS, 0, s>>>(
         P, grid_x, sorted_ids, reinterpret_cast<const uint2*>(sorted_rects), block_offsets, keys32_out, vals_out, hist,
-        tile_bits, n_sorted, 0, nullptr, 0, nullptr);
+        tile_bits, n_sorted, 0, nullptr, 0, nullptr, 0);
     cudaError_t e = cudaPeekAtLastError();
     return e == cudaSuccess ? 1 : -(int)e;
 }
@@ -522,14 +540,14 @@ size_t duplicate_fused_state_bytes(int P) { return ((size_t)num_dup_blocks(P) + 
 
 int launch_duplicate_fused(int P, int grid_x, const uint32_t* sorted_ids, const uint32_t* tile_rects, bool coarse,
                            void* fuse_state, uint32_t* keys32_out, uint32_t* vals_out, uint32_t* hist, int tile_bits,
-                           cudaStream_t s, const uint32_t* n_sorted, uint32_t* error_flag) {
+                           cudaStream_t s, const uint32_t* n_sorted, uint32_t* error_flag, bool rects_presorted) {
     if (P <= 0) return 0;
     if (tile_bits < 1 || tile_bits > 32 || !fuse_state) return GSR_ERR_INVALID_ARG;
     const int blocks = num_dup_blocks(P);
     GSR_CARVEOUT(duplicate_sorted_kernel<true>, "DUP", -1);
     duplicate_sorted_kernel<true><<<blocks, PRE_THREADS, 0, s>>>(
         P, grid_x, sorted_ids, reinterpret_cast<const uint2*>(tile_rects), nullptr, keys32_out, vals_out, hist, tile_bits,
-        n_sorted, coarse ? 1 : 0, static_cast<unsigned long long*>(fuse_state), blocks, error_flag);
+        n_sorted, coarse ? 1 : 0, static_cast<unsigned long long*>(fuse_state), blocks, error_flag, rects_presorted ? 1 : 0);
     cudaError_t e = cudaPeekAtLastError();
     return e == cudaSuccess ? 1 : -(int)e;
 }

@@ -215,6 +215,13 @@ int gsr_forward_ex(const gsr_forward_args* a) { return gsr::forward_impl(a, null
 #ifndef GSR_FUSED_DUP
 #define GSR_FUSED_DUP 0
 #endif
+// GSR_FUSED_SORT=1 (default): lean calls let the LAST depth pass of the sort bring the tile rects into depth order
+// (Sort32Plan::rect_dst) and the duplication find its offsets by look-back over those presorted rects: the
+// gather_rects launch and the single-CTA scan behind it disappear from the frame (profiles/r02_ab.txt).  Callers that
+// want point_offsets materialised (no GSR_FLAG_LEAN_STATE) keep the separate kernels, which also produce that array.
+#ifndef GSR_FUSED_SORT
+#define GSR_FUSED_SORT 1
+#endif
 // every stage launcher returns the number of kernels it launched, or a negative error
 #define GSR_STAGE(call)       \
     do {                      \
@@ -271,7 +278,7 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
     const int depth_passes = sort_num_passes(32);
 
     uint32_t R = 0, Rc = 0;
-    bool fused_dup = false;
+    bool fused_dup = false, fused_sort = false;
     const uint32_t* n_depth = nullptr;  // device: Gaussians the depth sort kept
     uint32_t* sort_error = nullptr;     // device address of the slot's sticky error word
     tm.mark();  // 0
@@ -306,7 +313,8 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         if (lean) { pp.cov3D = nullptr; pp.clamped = nullptr; pp.tiles_touched = nullptr; }
         // lean callers need no point_offsets, so the duplication can gather its rects and find its offsets itself
         // (binning.cu, duplicate_sorted_kernel<true>) instead of running behind gather_rects + a single-CTA scan
-        fused_dup = lean && GSR_FUSED_DUP != 0;
+        fused_sort = lean && GSR_FUSED_SORT != 0;
+        fused_dup = fused_sort || (lean && GSR_FUSED_DUP != 0);
         if (fused_dup) GSR_CUDA_TRY(cudaMemsetAsync(geom.sorted_block_sums, 0, duplicate_fused_state_bytes(P), s));
         // all clears of the frame up front, so the kernels behind them form uninterrupted dependent-launch chains
         if (!sort32_prepare(geom.depth_sort_space, (size_t)P, 32, s)) return -(int)cudaGetLastError();
@@ -331,6 +339,10 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         // Gaussians that emit nothing carry the key 0xffffffff (preprocess): the sort drops them, so its later
         // passes, the rect gather and the duplication only see the n_depth <= P Gaussians that are on screen
         dp.drop_pad = true;
+        if (fused_sort) {
+            dp.rect_src = geom.tile_rects; dp.rect_dst = geom.sorted_rects; dp.rect_coarse = bin_mode;
+            dp.keys_out = nullptr;  // nothing downstream reads the sorted depth keys
+        }
         n_depth = sort32_kept_count(geom.depth_sort_space, (size_t)P, 32);
         GSR_STAGE(launch_sort32(dp, s, sort_ev));
         // tile rects into depth order + scan of the per-block pair counts (same total, other order)
@@ -388,9 +400,9 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         uint32_t* bin_hist = sort32_prepare(tile_temp, (size_t)Rc, bin_bits, s);
         if (!bin_hist) return -(int)cudaGetLastError();
         if (fused_dup)
-            GSR_STAGE(launch_duplicate_fused(P, bins_x, geom.depth_sort_ids[1], geom.tile_rects, /*coarse=*/true,
-                                             geom.sorted_block_sums, k32[0], v32[0], bin_hist, bin_bits, s, n_depth,
-                                             sort_error));
+            GSR_STAGE(launch_duplicate_fused(P, bins_x, geom.depth_sort_ids[1], fused_sort ? geom.sorted_rects : geom.tile_rects,
+                                             /*coarse=*/true, geom.sorted_block_sums, k32[0], v32[0], bin_hist, bin_bits, s,
+                                             n_depth, sort_error, /*rects_presorted=*/fused_sort));
         else
             GSR_STAGE(launch_duplicate_sorted(P, bins_x, geom.depth_sort_ids[1], geom.sorted_rects, geom.sorted_block_sums,
                                               k32[0], v32[0], bin_hist, bin_bits, s, n_depth));
@@ -426,9 +438,9 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         uint32_t* tile_hist = sort32_prepare(tile_temp, (size_t)R, tile_bits, s);
         if (!tile_hist) return -(int)cudaGetLastError();
         if (fused_dup)
-            GSR_STAGE(launch_duplicate_fused(P, gx, geom.depth_sort_ids[1], geom.tile_rects, /*coarse=*/false,
-                                             geom.sorted_block_sums, k32[0], v32[0], tile_hist, tile_bits, s, n_depth,
-                                             sort_error));
+            GSR_STAGE(launch_duplicate_fused(P, gx, geom.depth_sort_ids[1], fused_sort ? geom.sorted_rects : geom.tile_rects,
+                                             /*coarse=*/false, geom.sorted_block_sums, k32[0], v32[0], tile_hist, tile_bits, s,
+                                             n_depth, sort_error, /*rects_presorted=*/fused_sort));
         else
             GSR_STAGE(launch_duplicate_sorted(P, gx, geom.depth_sort_ids[1], geom.sorted_rects, geom.sorted_block_sums, k32[0],
                                               v32[0], tile_hist, tile_bits, s, n_depth));

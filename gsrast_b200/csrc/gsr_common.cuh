@@ -87,12 +87,14 @@ int launch_duplicate_sorted(int P, int grid_x, const uint32_t* sorted_ids, const
                             const uint32_t* block_offsets, uint32_t* keys32_out, uint32_t* vals_out, uint32_t* hist,
                             int tile_bits, cudaStream_t s, const uint32_t* n_sorted = nullptr);
 // Fused form for callers that do not need point_offsets: gathers the rects by id itself (tile_rects; coarse = emit
-// (bin, Gaussian) records) and finds its offsets by decoupled look-back; `fuse_state` = duplicate_fused_state_bytes(P)
+// (bin, Gaussian) records) — or, rects_presorted, reads them already in depth order and final units from `tile_rects`
+// (the last depth pass of the sort left them there, Sort32Plan::rect_dst) — and finds its offsets by decoupled look-back; `fuse_state` = duplicate_fused_state_bytes(P)
 // zeroed bytes.  Replaces launch_gather_rects + the scan of its block sums + launch_duplicate_sorted.
 size_t duplicate_fused_state_bytes(int P);
 int launch_duplicate_fused(int P, int grid_x, const uint32_t* sorted_ids, const uint32_t* tile_rects, bool coarse,
                            void* fuse_state, uint32_t* keys32_out, uint32_t* vals_out, uint32_t* hist, int tile_bits,
-                           cudaStream_t s, const uint32_t* n_sorted = nullptr, uint32_t* error_flag = nullptr);
+                           cudaStream_t s, const uint32_t* n_sorted = nullptr, uint32_t* error_flag = nullptr,
+                           bool rects_presorted = false);
 // zero_first: clear ranges[num_tiles] here (otherwise the caller has already done it)
 int launch_identify_ranges(const uint64_t* keys, size_t n, uint32_t* ranges, int num_tiles, bool compat,
                            cudaStream_t s, bool zero_first = true);
@@ -129,6 +131,11 @@ struct Sort32Plan {
     // the later passes and every consumer work on the first sort32_kept_count() entries of the output only
     // (the rest of the output arrays is undefined).  Needs >= 2 passes and !hist_ready.
     bool drop_pad;
+    // last pass only, optional: also write rect_dst[g] = rect_src[value] (uint2; coarse: converted to bin units) for the
+    // item landing at g — the tile rects in sorted order; keys_out may then be nullptr.  Needs >= 2 passes.
+    const uint32_t* rect_src;
+    uint32_t* rect_dst;
+    bool rect_coarse;
     // device word the look-back watchdog sets when it trips (nullptr: a word inside `temp`, which nobody reads back)
     uint32_t* error_flag;
 };

@@ -174,6 +174,12 @@ struct PassArgs {
     // last tile-digit pass of the forward path: key64 = key32 << 32 | expand_low[value]
     const uint32_t* expand_low;
     uint64_t* keys_out64;
+    // RECTS (last depth pass of the forward path, lean callers): the pass also brings the tile rects into the sorted
+    // order — rect_dst[g] = rect_src[value] for the item that lands at position g (coarse: in units of bins) — which is
+    // what gather_rects_kernel did in a launch of its own; keys_out may then be null (nothing reads the sorted keys)
+    const uint2* rect_src;
+    uint2* rect_dst;
+    int rect_coarse;
 };
 
 // Shared memory: [SORT_TILE] key staging | [SORT_TILE] u32 value staging | per-warp digit counters
@@ -185,10 +191,11 @@ constexpr size_t onesweep_smem() {
 
 // DROP: items whose key is the all-ones pad value are neither counted nor written (the output is compacted);
 // the tile then stages n_stage <= n_tile items.
-template <typename KeyT, bool EXPAND, bool FULL, int SORT_ITEMS, bool DROP>
+template <typename KeyT, bool EXPAND, bool FULL, int SORT_ITEMS, bool DROP, bool RECTS>
 __device__ __forceinline__ void onesweep_tile(const PassArgs& a, const uint32_t n_tile, const uint32_t tile,
                                               unsigned char* s_raw) {
     static_assert(!(DROP && FULL), "a dropping pass tests every item");
+    static_assert(!(RECTS && EXPAND), "the rect gather belongs to the last depth pass, the key expansion to the last tile pass");
     constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
     KeyT* s_keys = reinterpret_cast<KeyT*>(s_raw);                                             // [SORT_TILE]
     uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_raw + (size_t)SORT_TILE * sizeof(KeyT));  // [SORT_TILE]
@@ -415,6 +422,27 @@ __device__ __forceinline__ void onesweep_tile(const PassArgs& a, const uint32_t 
                 a.vals_out[g] = s_vals[j];
             }
         }
+    } else if (RECTS) {
+        // every rect gather of the thread is in flight before the first one is used (the only random access of the
+        // pass; 8 bytes per Gaussian out of an array preprocess wrote a few hundred microseconds ago)
+        uint2 rc[SORT_ITEMS];
+#pragma unroll
+        for (int k = 0; k < SORT_ITEMS; ++k) {
+            const uint32_t j = tid + k * SORT_THREADS;
+            rc[k] = (FULL || j < n_stage) ? __ldg(a.rect_src + s_vals[j]) : make_uint2(0u, 0u);
+        }
+        KeyT* kout = reinterpret_cast<KeyT*>(a.keys_out);
+#pragma unroll
+        for (int k = 0; k < SORT_ITEMS; ++k) {
+            const uint32_t j = tid + k * SORT_THREADS;
+            if (FULL || j < n_stage) {
+                const KeyT kk = s_keys[j];
+                const uint32_t g = s_global[digit_of(kk, shift, dmask)] + j;
+                if (kout) kout[g] = kk;
+                a.vals_out[g] = s_vals[j];
+                a.rect_dst[g] = a.rect_coarse ? coarse_rect(rc[k]) : rc[k];
+            }
+        }
     } else {
         KeyT* kout = reinterpret_cast<KeyT*>(a.keys_out);
 #pragma unroll
@@ -430,7 +458,7 @@ __device__ __forceinline__ void onesweep_tile(const PassArgs& a, const uint32_t 
     }
 }
 
-template <typename KeyT, bool EXPAND, int MIN_BLOCKS, int SORT_ITEMS, bool DROP = false>
+template <typename KeyT, bool EXPAND, int MIN_BLOCKS, int SORT_ITEMS, bool DROP = false, bool RECTS = false>
 __global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) onesweep_kernel(const PassArgs a) {
     constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -453,11 +481,11 @@ __global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) onesweep_kernel(cons
     if (tile_base >= n) return;
     const uint32_t n_tile = (uint32_t)min((size_t)SORT_TILE, n - tile_base);
     if (DROP)
-        onesweep_tile<KeyT, EXPAND, false, SORT_ITEMS, true>(a, n_tile, tile, s_raw);
+        onesweep_tile<KeyT, EXPAND, false, SORT_ITEMS, true, RECTS>(a, n_tile, tile, s_raw);
     else if (n_tile == SORT_TILE)
-        onesweep_tile<KeyT, EXPAND, true, SORT_ITEMS, false>(a, n_tile, tile, s_raw);
+        onesweep_tile<KeyT, EXPAND, true, SORT_ITEMS, false, RECTS>(a, n_tile, tile, s_raw);
     else
-        onesweep_tile<KeyT, EXPAND, false, SORT_ITEMS, false>(a, n_tile, tile, s_raw);
+        onesweep_tile<KeyT, EXPAND, false, SORT_ITEMS, false, RECTS>(a, n_tile, tile, s_raw);
 }
 
 size_t num_sort_tiles(size_t n, int items) { return (n + (size_t)SORT_THREADS * items - 1) / ((size_t)SORT_THREADS * items); }
@@ -510,7 +538,7 @@ int launch_histogram(const KeyT* keys, size_t n, int end_bit, int passes, uint32
     return 1;
 }
 
-template <typename KeyT, bool EXPAND, int MIN_BLOCKS, int ITEMS, bool DROP = false>
+template <typename KeyT, bool EXPAND, int MIN_BLOCKS, int ITEMS, bool DROP = false, bool RECTS = false>
 int launch_pass(const PassArgs& a, cudaStream_t s) {
     constexpr size_t smem = onesweep_smem<KeyT, ITEMS>();
     // per-device attribute (one process may drive several GPUs): set once per device and instantiation
@@ -519,12 +547,12 @@ int launch_pass(const PassArgs& a, cudaStream_t s) {
     GSR_CUDA_TRY(cudaGetDevice(&dev));
     const uint64_t bit = 1ull << (dev & 63);
     if (!(configured.load(std::memory_order_acquire) & bit)) {
-        GSR_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS, ITEMS, DROP>,
+        GSR_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS, ITEMS, DROP, RECTS>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured.fetch_or(bit, std::memory_order_release);
     }
-    GSR_CARVEOUT((onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS, ITEMS, DROP>), "SORT", -1);
-    GSR_CUDA_TRY(launch_pdl(onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS, ITEMS, DROP>,
+    GSR_CARVEOUT((onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS, ITEMS, DROP, RECTS>), "SORT", -1);
+    GSR_CUDA_TRY(launch_pdl(onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS, ITEMS, DROP, RECTS>,
                             dim3((unsigned)num_sort_tiles(a.n, ITEMS)), dim3(SORT_THREADS), smem, s, a));
     return 1;
 }
@@ -578,6 +606,7 @@ int launch_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint
         a.ticket = L.tickets + ps;
         a.error_flag = error_flag ? error_flag : L.tickets + MAX_PASSES;
         a.expand_low = nullptr; a.keys_out64 = nullptr;
+        a.rect_src = nullptr; a.rect_dst = nullptr; a.rect_coarse = 0;
         int rc = launch_pass<uint2, false, 2, ITEMS_LARGE>(a, s);
         if (rc < 0) return rc;
         ++launches;
@@ -633,6 +662,7 @@ int launch_sort32(const Sort32Plan& p, cudaStream_t s, cudaEvent_t* events) {
         a.ticket = L.tickets + ps;
         a.error_flag = p.error_flag ? p.error_flag : L.tickets + MAX_PASSES;
         a.expand_low = nullptr; a.keys_out64 = nullptr;
+        a.rect_src = nullptr; a.rect_dst = nullptr; a.rect_coarse = 0;
         int rc;
         if (kept && ps == 0) {
             a.keys_out = p.kbuf[0]; a.vals_out = p.vbuf[0];
@@ -645,6 +675,12 @@ int launch_sort32(const Sort32Plan& p, cudaStream_t s, cudaEvent_t* events) {
                 a.expand_low = p.expand_low; a.keys_out64 = p.keys_out64;
                 rc = items == ITEMS_SMALL ? launch_pass<uint32_t, true, 4, ITEMS_SMALL>(a, s)
                                           : launch_pass<uint32_t, true, GSR_MINB_LARGE - 1, ITEMS_LARGE>(a, s);
+            } else if (p.rect_src) {
+                a.rect_src = reinterpret_cast<const uint2*>(p.rect_src);
+                a.rect_dst = reinterpret_cast<uint2*>(p.rect_dst);
+                a.rect_coarse = p.rect_coarse ? 1 : 0;
+                rc = items == ITEMS_SMALL ? launch_pass<uint32_t, false, 6, ITEMS_SMALL, false, true>(a, s)
+                                          : launch_pass<uint32_t, false, GSR_MINB_LARGE, ITEMS_LARGE, false, true>(a, s);
             } else {
                 rc = items == ITEMS_SMALL ? launch_pass<uint32_t, false, 6, ITEMS_SMALL>(a, s)
                                           : launch_pass<uint32_t, false, GSR_MINB_LARGE, ITEMS_LARGE>(a, s);

@@ -45,6 +45,18 @@ def check_properties(cu, P, W, H):
     assert np.all(cu["n_contrib"].reshape(H, W) <= counts[per_pixel_tile])
 
 
+def assert_lean_path_identical(sc, cam, full, **kw):
+    """GSR_FLAG_LEAN_STATE (what gsr_renderer_* and therefore bench.py run): the last depth pass gathers the rects and
+    the duplication finds its offsets by look-back instead of gather_rects + scan — every output of the pass must be
+    the same bits as the full-state call's."""
+    from gsrast_b200 import _lib
+
+    lean = run_cuda(sc, cam, flags=_lib.FLAG_LEAN_STATE, **kw)
+    assert lean["num_rendered"] == full["num_rendered"]
+    for k in ("radii", "keys", "values", "ranges", "n_contrib", "final_T", "out_color"):
+        assert np.array_equal(lean[k], full[k]), k
+
+
 def test_c2_full_size_exact(oracle):
     """3.3M Gaussians SH3 @ 1920x1080 — the metric's configuration — against the oracle."""
     sc, cfg = S.make_config_scene("C2")
@@ -57,6 +69,7 @@ def test_c2_full_size_exact(oracle):
     cu2 = run_cuda(sc, cam, use_rects=False)
     assert np.array_equal(cu2["keys"], cu["keys"]) and np.array_equal(cu2["values"], cu["values"])
     assert np.array_equal(cu2["out_color"], cu["out_color"])
+    assert_lean_path_identical(sc, cam, cu)
 
 
 def test_c5_full_size_exact(oracle):
@@ -69,6 +82,7 @@ def test_c5_full_size_exact(oracle):
     check_properties(cu, sc.P, cfg["W"], cfg["H"])
     ref = run_oracle(oracle, sc, cam)
     assert_parity(cu, ref, colours_from_sh=False)
+    assert_lean_path_identical(sc, cam, cu)
     simple = run_cuda(sc, cam, flags=FLAG_BLEND_SIMPLE)
     assert np.abs(simple["out_color"] - cu["out_color"]).max() <= 1.0 / 255.0
     assert psnr(simple["out_color"], cu["out_color"]) >= 50.0
@@ -87,3 +101,4 @@ def test_c3_full_size_exact(oracle, compat):
     if compat:  # un-clamped DC colours 0.5 + 0.4*sh leave [0,1] (GSCuda.cu:364-365)
         cmax = float(np.abs(ref.rgb[ref.radii > 0]).max())
     assert_parity(cu, ref, colour_max=cmax)
+    assert_lean_path_identical(sc, cam, cu, compat=compat, use_rects=compat)

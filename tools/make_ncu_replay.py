@@ -60,9 +60,11 @@ def main():
                 res["dram_bytes"] = res["dram_rd_bytes"] + res.get("dram_wr_bytes", 0)
             name = short_name(full)
             tmpl = re.search(r"<([^()]*)>\(", full)
-            key = name if li == 0 or name not in kernels else "%s#%d" % (name, li)
             res["template_args"] = tmpl.group(1) if tmpl else None
             res["report"] = os.path.basename(path)
+            # the first launch of every kernel; further instantiations of the same kernel under "name<args>"
+            key = name if name not in kernels or kernels[name]["template_args"] == res["template_args"] else \
+                "%s<%s>" % (name, res["template_args"])
             kernels.setdefault(key, res)
             lines.append("%s %s" % (os.path.basename(path), dict(kernel=name + ("<%s>" % res["template_args"] if tmpl else ""), **{k: v for k, v in res.items() if k not in ("template_args", "report")})))
     out = {"_source": "ncu --set full --clock-control none, one launch per kernel after warm-up (tools/gpu_prof_all.sh); "

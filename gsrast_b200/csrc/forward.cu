@@ -215,12 +215,14 @@ int gsr_forward_ex(const gsr_forward_args* a) { return gsr::forward_impl(a, null
 #ifndef GSR_FUSED_DUP
 #define GSR_FUSED_DUP 0
 #endif
-// GSR_FUSED_SORT=1 (default): lean calls let the LAST depth pass of the sort bring the tile rects into depth order
-// (Sort32Plan::rect_dst) and the duplication find its offsets by look-back over those presorted rects: the
-// gather_rects launch and the single-CTA scan behind it disappear from the frame (profiles/r02_ab.txt).  Callers that
-// want point_offsets materialised (no GSR_FLAG_LEAN_STATE) keep the separate kernels, which also produce that array.
+// GSR_FUSED_SORT=1: lean calls let the LAST depth pass of the sort bring the tile rects into depth order
+// (Sort32Plan::rect_dst) and the duplication find its offsets by look-back over those presorted rects, so the
+// gather_rects launch and the single-CTA scan behind it disappear from the frame.  Built, parity-green (76 GPU tests),
+// and measured SLOWER (profiles/r02f_ab_C2.txt: the pass with 16 random 8-byte gathers per thread takes 93-106 us
+// instead of 32, the look-back duplication 48 instead of 33; 1315 vs 1383 frames/s): gather_rects at 88 % occupancy
+// hides the DRAM latency of that gather far better than 32 warps per SM in the tail of a sort pass can.  Off.
 #ifndef GSR_FUSED_SORT
-#define GSR_FUSED_SORT 1
+#define GSR_FUSED_SORT 0
 #endif
 // every stage launcher returns the number of kernels it launched, or a negative error
 #define GSR_STAGE(call)       \

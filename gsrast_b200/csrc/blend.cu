@@ -431,6 +431,17 @@ __device__ __forceinline__ u64 sub2(u64 a, u64 b) {
     return d;
 }
 
+// GSR_PAIR_PREDCOL=1: colour accumulation as six predicated scalar FFMAs (FMA pipe) instead of two weight selects (ALU
+// pipe) + three FFMA2 — one issue slot more per trip, two half-rate ALU instructions fewer; GSR_PAIR_UNROLL: trips per
+// loop iteration.  Measured C2 / C5 blend (profiles/r02g_ab_*.txt): packed colour, unroll 2: 0.262 / 1.055 ms; unroll 4:
+// 0.255 / 1.036; predicated colour: 0.251 / 1.018; both: 0.251 / 1.015.
+#ifndef GSR_PAIR_PREDCOL
+#define GSR_PAIR_PREDCOL 1
+#endif
+#ifndef GSR_PAIR_UNROLL
+#define GSR_PAIR_UNROLL 4
+#endif
+constexpr int PAIR_UNROLL = GSR_PAIR_UNROLL;
 constexpr int PAIR_THREADS = 128;
 constexpr int PAIR_WARPS = PAIR_THREADS / 32;
 static_assert(CBATCH == PAIR_THREADS, "every thread of the pair kernel stages one splat per round");
@@ -469,7 +480,11 @@ __global__ void __launch_bounds__(PAIR_THREADS, GSR_PAIR_MINB) blend_pair_kernel
 
     // pixels outside the image start "terminated" (negative T, see blend_culled_kernel)
     float T0 = inside0 ? 1.0f : -1.0f, T1 = inside1 ? 1.0f : -1.0f;
+#if GSR_PAIR_PREDCOL
+    float c00 = 0.f, c01 = 0.f, c10 = 0.f, c11 = 0.f, c20 = 0.f, c21 = 0.f;  // channel x pixel
+#else
     u64 C0 = 0ull, C1 = 0ull, C2 = 0ull;  // {pixel 0, pixel 1} per channel
+#endif
     uint32_t last0 = 0, last1 = 0;
     bool warp_done = __all_sync(0xffffffffu, !inside0 && !inside1);
 
@@ -554,7 +569,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, GSR_PAIR_MINB) blend_pair_kernel
             uint32_t last_off0 = 0xffffffffu, last_off1 = 0xffffffffu;
             for (int i0 = 0; i0 < n; i0 += 16) {
                 const int i1 = min(n, i0 + 16);
-#pragma unroll 2
+#pragma unroll PAIR_UNROLL
                 for (int i = i0; i < i1; ++i) {
                     const uint32_t rec = lds16(list_base + 2u * (uint32_t)i);
                     const float4 a = lds128(rec);        // x, y, a', b'
@@ -580,12 +595,16 @@ __global__ void __launch_bounds__(PAIR_THREADS, GSR_PAIR_MINB) blend_pair_kernel
                     float w0, w1, tt0, tt1;
                     unpk2(w2, w0, w1);
                     unpk2(tt2, tt0, tt1);
-                    // The decision tail of a pixel: 4 FSETP + 2 FSEL + 1 SEL on the ALU pipe (the busiest pipe of this
-                    // kernel).  An inline-PTX form with a two-destination setp (ok | stop from one compare) and
-                    // predicated moves was tried: ptxas turns it back into FSETP + PLOP3 + four selects — dropped.
+                    // The decision tail of a pixel.  The ALU pipe (FSETP / FSEL / FMNMX / SEL, half rate) is the busiest
+                    // pipe of this kernel (ncu: 58 %), so the tail is written with THREE compares per pixel: `ok` takes
+                    // `cand` as its predicate input, and under `cand` the transmittance select needs `ok` only (ok ==
+                    // pass there).  Tried and dropped: T' = T - wm as a packed FADD2 with a predicated
+                    // -|T| for the stop (ptxas keeps a select: 42 slots per trip instead of 39); an inline-PTX
+                    // two-destination setp (ptxas turns it back into FSETP + PLOP3 + selects); `last` copied by a
+                    // predicated FMUL x*1 on the FMA pipe (ptxas hoists the multiply and selects); a warp-uniform branch
+                    // around the two FMNMX for splats with opacity <= 0.99 (if-converted to predicated FMNMX).
                     const bool cand0 = (p0 <= 0.0f) && (al0 >= ALPHA_MIN), cand1 = (p1 <= 0.0f) && (al1 >= ALPHA_MIN);
-                    const bool pass0 = tt0 >= t_min, pass1 = tt1 >= t_min;
-                    const bool ok0 = cand0 && pass0, ok1 = cand1 && pass1;
+                    const bool ok0 = cand0 && (tt0 >= t_min), ok1 = cand1 && (tt1 >= t_min);
                     if (COUNT) {
                         ++c_trips;
                         c_live += (T0 > 0.0f) + (T1 > 0.0f);
@@ -594,14 +613,19 @@ __global__ void __launch_bounds__(PAIR_THREADS, GSR_PAIR_MINB) blend_pair_kernel
                     }
                     if (ok0) last_off0 = rec;
                     if (ok1) last_off1 = rec;
+                    // blended -> T(1 - alpha); would fall below t_min -> stop, keeping the final T as -|T|
+                    if (cand0) T0 = ok0 ? tt0 : -fabsf(T0);
+                    if (cand1) T1 = ok1 ? tt1 : -fabsf(T1);
+#if GSR_PAIR_PREDCOL
+                    if (ok0) { c00 = fmaf(b.z, w0, c00); c10 = fmaf(b.w, w0, c10); c20 = fmaf(cb3, w0, c20); }
+                    if (ok1) { c01 = fmaf(b.z, w1, c01); c11 = fmaf(b.w, w1, c11); c21 = fmaf(cb3, w1, c21); }
+#else
                     // a pixel that does not blend this splat adds +0 * colour (its weight is selected to zero)
-                    const float wm0 = ok0 ? w0 : 0.0f, wm1 = ok1 ? w1 : 0.0f;
-                    if (cand0) T0 = pass0 ? tt0 : -fabsf(T0);
-                    if (cand1) T1 = pass1 ? tt1 : -fabsf(T1);
-                    const u64 wm2 = pk2(wm0, wm1);
+                    const u64 wm2 = pk2(ok0 ? w0 : 0.0f, ok1 ? w1 : 0.0f);
                     C0 = fma2(pk2(b.z, b.z), wm2, C0);
                     C1 = fma2(pk2(b.w, b.w), wm2, C1);
                     C2 = fma2(pk2(cb3, cb3), wm2, C2);
+#endif
                 }
                 if (__all_sync(0xffffffffu, T0 <= 0.0f && T1 <= 0.0f)) {
                     warp_done = true;
@@ -625,10 +649,12 @@ __global__ void __launch_bounds__(PAIR_THREADS, GSR_PAIR_MINB) blend_pair_kernel
     }
     T0 = fabsf(T0);
     T1 = fabsf(T1);
+#if !GSR_PAIR_PREDCOL
     float c00, c01, c10, c11, c20, c21;
     unpk2(C0, c00, c01);
     unpk2(C1, c10, c11);
     unpk2(C2, c20, c21);
+#endif
     const size_t plane = (size_t)p.W * p.H;
     const float bg0 = __ldg(p.background + 0), bg1 = __ldg(p.background + 1), bg2 = __ldg(p.background + 2);
     if (inside0) {

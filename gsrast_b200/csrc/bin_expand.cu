@@ -38,6 +38,14 @@ namespace {
 #ifndef GSR_FILL_FAST
 #define GSR_FILL_FAST 1
 #endif
+// GSR_FILL_BALANCED=1: every thread of the fill pass takes 8 CONSECUTIVE staged slots and finds its position by search
+// (tile offset, warp-step prefix, rank in the ballot) instead of walking the ballots of one (tile, quarter).  Built,
+// parity-green, measured SLOWER (profiles/r02i_ab_*.txt: fill 0.107 vs 0.088 ms at C2, 0.381 vs 0.353 ms expansion at
+// C3): the nine dependent shared-memory loads of the search and the single-warp table build cost more than the idle
+// lanes of the walk they replace.  Off.
+#ifndef GSR_FILL_BALANCED
+#define GSR_FILL_BALANCED 0
+#endif
 constexpr int EXP_THREADS = 256;
 constexpr int EXP_WARPS = EXP_THREADS / 32;
 constexpr int EXP_CHUNK = 256;                 // records per chunk: one per thread, one warp-step (32 records) per warp
@@ -493,7 +501,86 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_fill_kernel(const ExpandAr
         if (tid < BIN_TILES) { s_gbase[tid] = gb; s_tileid[tid] = tile; }
     }
     __syncthreads();
-#if GSR_FILL_FAST
+#if GSR_FILL_BALANCED
+    // Balanced single-round path (chunks of at most EXP_CAP pairs, i.e. nearly all of them).  The pairs of the chunk
+    // form one staged sequence — tile-major, then warp-step, then lane: the sorted order — and every thread takes
+    // FILL_ITEMS CONSECUTIVE slots of it: one search (tile by its offset, warp-step by the tile's prefix, rank inside
+    // the ballot) positions the thread, then it walks set bits across ballot / tile boundaries.  Every thread does the
+    // same amount of work whatever the shape of the rects, where the thread-per-(tile, quarter) walk below leaves most
+    // lanes of a warp idle (tiles at the edge of a rect list few records): ~130 thread-slots per pair there.
+    {
+        constexpr int FILL_ITEMS = EXP_CAP / EXP_THREADS;  // 8
+        if (warp == 0) {
+            // per tile: prefix over the warp-steps; exclusive scan of the tile totals over the 64 tiles (lane, 32 + lane)
+            uint32_t run0 = 0, run1 = 0;
+#pragma unroll
+            for (int ws = 0; ws < EXP_WS; ++ws) {
+                s_pre[ws][lane] = run0;
+                s_pre[ws][32 + lane] = run1;
+                run0 += (uint32_t)__popc(s_bal[ws][lane]);
+                run1 += (uint32_t)__popc(s_bal[ws][32 + lane]);
+            }
+            s_pre[EXP_WS][lane] = run0;
+            s_pre[EXP_WS][32 + lane] = run1;
+            uint32_t i0 = run0, i1 = run1;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const uint32_t t0 = __shfl_up_sync(0xffffffffu, i0, dd);
+                const uint32_t t1 = __shfl_up_sync(0xffffffffu, i1, dd);
+                if (lane >= dd) { i0 += t0; i1 += t1; }
+            }
+            const uint32_t tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
+            const uint32_t o0 = i0 - run0, o1 = tot0 + i1 - run1;
+            s_soff[lane] = o0;
+            s_soff[32 + lane] = o1;
+            s_gadj[lane] = s_gbase[lane] - o0;  // final position = s_gadj[t] + staged index
+            s_gadj[32 + lane] = s_gbase[32 + lane] - o1;
+            if (lane == 0) s_round_pairs = tot0 + tot1;
+        }
+        __syncthreads();
+        const uint32_t total = s_round_pairs;
+        if (total <= (uint32_t)EXP_CAP) {
+            const uint32_t s0 = (uint32_t)tid * FILL_ITEMS;
+            if (s0 < total) {
+                // tile: the largest t with s_soff[t] <= s0 (empty tiles share their successor's offset, so this is the owner)
+                int t = 0;
+#pragma unroll
+                for (int step = BIN_TILES / 2; step >= 1; step >>= 1)
+                    if (s_soff[t + step] <= s0) t += step;
+                uint32_t r = s0 - s_soff[t];
+                int ws = 0;
+#pragma unroll
+                for (int step = EXP_WS / 2; step >= 1; step >>= 1)
+                    if (s_pre[ws + step][t] <= r) ws += step;
+                r -= s_pre[ws][t];
+                uint32_t bits = s_bal[ws][t];
+                for (; r > 0; --r) bits &= bits - 1u;  // drop the set bits that belong to the slots before s0
+                const uint32_t n_mine = min((uint32_t)FILL_ITEMS, total - s0);
+                for (uint32_t i = 0; i < n_mine; ++i) {
+                    while (bits == 0u) {  // next warp-step, next tile (s0 + i < total: there is one)
+                        if (++ws == EXP_WS) { ws = 0; ++t; }
+                        bits = s_bal[ws][t];
+                    }
+                    const int l = __ffs((int)bits) - 1;
+                    bits &= bits - 1u;
+                    const uint32_t slot = s0 + i;
+                    s_out[slot ^ ((slot >> 4) & 7u)] = s_rec[ws * 32 + l];  // XOR swizzle: 2-way instead of 16-way conflicts
+                    s_t[slot] = (unsigned char)t;
+                }
+            }
+            __syncthreads();
+            for (uint32_t j = tid; j < total; j += EXP_THREADS) {
+                const int tt = s_t[j];
+                const uint32_t g = s_gadj[tt] + j;
+                const uint2 o2 = s_out[j ^ ((j >> 4) & 7u)];
+                a.keys_out[g] = ((uint64_t)s_tileid[tt] << 32) | (uint64_t)o2.y;  // GSCuda.cu:466-471
+                a.vals_out[g] = o2.x;
+            }
+            return;
+        }
+        __syncthreads();  // a big chunk: the rounds below rebuild their tables
+    }
+#elif GSR_FILL_FAST
     // Fast path (chunks of at most EXP_CAP pairs, i.e. nearly all of them): a single round, no further table
     // building.  Thread (tile t = tid & 63, quarter q) has t = 32 * (warp & 1) + lane, so every warp derives what
     // its threads need from the ballots on its own — its half's per-tile counts (scanned across the lanes) and the

@@ -259,3 +259,57 @@ def test_lean_state_flag_changes_no_output_of_the_pass(oracle):
             assert np.array_equal(a, b), (extra, k)
         vis = full["radii"] > 0
         assert np.abs(full["cov3D"].reshape(-1, 6)[vis]).max() > 0  # the default call does fill it
+
+
+def test_pair_count_overflow_is_detected_on_the_device():
+    """140 000 Gaussians that each cover the whole 4K grid: 4.5e9 pairs.  The 32-bit sum the reference would use
+    (GSCuda.cu:771) wraps to ~2.4e8 — a plausible num_rendered for which the binning chunk would be sized and then
+    overrun.  The scan kernel's 64-bit total must turn this into GSR_ERR_TOO_MANY_PAIRS before the binning allocator
+    is ever called."""
+    import torch
+
+    from gsrast_b200 import _lib
+    from gsrast_b200 import rasterizer as R
+
+    P, W, H = 140_000, 3840, 2160
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(7)
+    means = (torch.rand((P, 3), generator=g) - 0.5) * 0.2
+    t = lambda a: a.to(dev).contiguous()  # noqa: E731
+    scales = torch.full((P, 3), 50.0)
+    rot = torch.tensor([1.0, 0.0, 0.0, 0.0]).repeat(P, 1)
+    cam = Cm.default_camera(W, H)
+    geom, binning, img = R.resize_functional(dev), R.resize_functional(dev), R.resize_functional(dev)
+    out = torch.zeros((3, H, W), device=dev)
+    keep = [t(means), t(torch.zeros((P, 16, 3))), t(torch.full((P,), 0.5)), t(scales), t(rot),
+            t(torch.from_numpy(cam.viewmatrix)), t(torch.from_numpy(cam.projmatrix)), t(torch.from_numpy(cam.cam_pos)),
+            torch.zeros(3, device=dev)]
+    with pytest.raises(RuntimeError) as ei:
+        R.Rasterizer.forward(geom, binning, img, P, 3, 16, keep[8], W, H, keep[0], keep[1], None, keep[2], keep[3], 1.0,
+                             keep[4], None, keep[5], keep[6], keep[7], cam.tan_fovx, cam.tan_fovy, False, out)
+    torch.cuda.synchronize()
+    assert str(_lib.ERR_TOO_MANY_PAIRS) in str(ei.value)
+    assert binning.calls == 0 and geom.calls == 1 and img.calls == 1
+    # the library is usable afterwards
+    sc = _scene("C1", 20_000)
+    cam2 = Cm.default_camera(640, 360)
+    assert run_cuda(sc, cam2)["num_rendered"] > 0
+
+
+def test_oversized_grid_is_rejected_before_any_allocation():
+    """More than 2^23 tiles (or more than 65535 tile columns / rows) would overflow the packed rects and the 32-bit
+    block sums: GSR_ERR_INVALID_ARG before a single allocator call."""
+    import torch
+
+    from gsrast_b200 import _lib
+    from gsrast_b200 import rasterizer as R
+
+    dev = torch.device("cuda")
+    dummy = torch.zeros(64, device=dev)
+    geom, binning, img = R.resize_functional(dev), R.resize_functional(dev), R.resize_functional(dev)
+    for W, H in ((50_000, 50_000), (16 * 70_000, 16)):
+        with pytest.raises(RuntimeError) as ei:
+            R.Rasterizer.forward(geom, binning, img, 1, 3, 16, dummy, W, H, dummy, dummy, None, dummy, dummy, 1.0, dummy,
+                                 None, dummy, dummy, dummy, 1.0, 1.0, False, dummy)
+        assert str(_lib.ERR_INVALID_ARG) in str(ei.value)
+    assert geom.calls == 0 and img.calls == 0 and binning.calls == 0

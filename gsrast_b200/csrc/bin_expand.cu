@@ -54,7 +54,12 @@ constexpr int EXP_CAP = 2048;                  // pairs staged per round (>= 32 
 constexpr int EXP_QUARTERS = EXP_THREADS / BIN_TILES;   // fill: thread = (tile, quarter of the warp-steps)
 constexpr int EXP_WS_PER_Q = EXP_WS / EXP_QUARTERS;
 constexpr int TABLE_THREADS = 1024;
-constexpr int SCAN_PARTS = EXP_THREADS / BIN_TILES;     // chunk scan: thread = (tile, part of the bin's chunks)
+#ifndef GSR_ESCAN_THREADS
+#define GSR_ESCAN_THREADS 1024   // 256: 25 us at C2 (the longest bin's column of chunk counts walked by 4 threads per tile)
+#endif
+constexpr int ESCAN_THREADS = GSR_ESCAN_THREADS;
+constexpr int ESCAN_WARPS = ESCAN_THREADS / 32;
+constexpr int SCAN_PARTS = ESCAN_THREADS / BIN_TILES;   // chunk scan: thread = (tile, part of the bin's chunks)
 
 __host__ __device__ inline size_t align128(size_t v) { return (v + 127) / 128 * 128; }
 
@@ -150,8 +155,11 @@ __device__ __forceinline__ uint32_t table_scan(const uint32_t v, uint32_t* s_war
 }
 
 // ---- chunk table --------------------------------------------------------------------------------
-// One CTA: per-bin record ranges (from the single-pass digit histogram `bin_counts`, or from bin_start
-// when the bin ids took two passes), chunks per bin, their exclusive scan, one descriptor per chunk.
+// Per-bin record ranges (from the single-pass digit histogram `bin_counts`, or from bin_start when the bin
+// ids took two passes), chunks per bin, their exclusive scan, one descriptor per chunk.  Every CTA of the
+// grid rebuilds the (tiny) per-bin tables in its shared memory and writes its share of the descriptors —
+// one CTA writing all 14 k descriptors of a C2 frame was a 12 us serial step of the frame's dependency chain;
+// CTA 0 alone publishes the per-bin tables and resets the scan's arrival counter.
 __global__ void __launch_bounds__(TABLE_THREADS) chunk_table_kernel(const int nbins, const uint32_t* __restrict__ bin_counts,
                                                                     uint32_t* __restrict__ bin_start,
                                                                     uint32_t* __restrict__ bin_chunk_first,
@@ -162,9 +170,10 @@ __global__ void __launch_bounds__(TABLE_THREADS) chunk_table_kernel(const int nb
     __shared__ uint32_t s_start[MAX_BINS + 1];
     __shared__ uint32_t s_first[MAX_BINS + 1];
     const int tid = threadIdx.x;
+    const bool lead = blockIdx.x == 0;
     gsr_pdl_wait();
     gsr_pdl_launch_dependents();
-    if (tid == 0) *done_counter = 0;
+    if (lead && tid == 0) *done_counter = 0;
     uint32_t cnt[PER], st[PER + 1], nch[PER], tsum = 0;
     if (bin_counts) {
 #pragma unroll
@@ -202,20 +211,24 @@ __global__ void __launch_bounds__(TABLE_THREADS) chunk_table_kernel(const int nb
         if (b < nbins) {
             s_start[b] = st[j];
             s_first[b] = run;
-            bin_chunk_first[b] = run;
-            if (bin_counts) bin_start[b] = st[j];
+            if (lead) {
+                bin_chunk_first[b] = run;
+                if (bin_counts) bin_start[b] = st[j];
+            }
             run += nch[j];
             if (b == nbins - 1) {
                 s_start[nbins] = st[j + 1];
                 s_first[nbins] = run;
-                bin_chunk_first[nbins] = run;  // number of chunks
-                if (bin_counts) bin_start[nbins] = st[j + 1];
+                if (lead) {
+                    bin_chunk_first[nbins] = run;  // number of chunks
+                    if (bin_counts) bin_start[nbins] = st[j + 1];
+                }
             }
         }
     }
     __syncthreads();
     // descriptors, one chunk per thread and round: bin by binary search over the first-chunk table
-    for (uint32_t k = tid; k < total; k += TABLE_THREADS) {
+    for (uint32_t k = blockIdx.x * TABLE_THREADS + tid; k < total; k += gridDim.x * TABLE_THREADS) {
         int lo = 0, hi = nbins - 1;  // largest b with s_first[b] <= k (empty bins share their successor's value)
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
@@ -345,14 +358,14 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_count_kernel(const ExpandA
 // order: tile_counts becomes the start of every tile's list and ranges[tile] = (start, start + count); a tile
 // nothing touches keeps (0, 0) exactly like the reference's cleared and never written entry (GSCuda.cu:800,
 // 504-538).
-__global__ void __launch_bounds__(EXP_THREADS) expand_scan_kernel(const uint32_t* __restrict__ bin_chunk_first,
+__global__ void __launch_bounds__(ESCAN_THREADS) expand_scan_kernel(const uint32_t* __restrict__ bin_chunk_first,
                                                                    uint32_t* __restrict__ chunk_counts,
                                                                    uint32_t* tile_counts, const int grid_x,
                                                                    const int grid_y, const int bins_x, const int nbins,
                                                                    uint2* __restrict__ ranges, const int r1_quirk,
                                                                    uint32_t* done_counter) {
     __shared__ uint32_t s_part[SCAN_PARTS][BIN_TILES];
-    __shared__ uint32_t s_warp[EXP_WARPS];
+    __shared__ uint32_t s_warp[ESCAN_WARPS];
     __shared__ uint32_t s_carry;
     __shared__ uint32_t s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -415,7 +428,7 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_scan_kernel(const uint32_t
     __syncthreads();
     const int tiles = grid_x * grid_y;
     constexpr int ITEMS = 8;
-    for (int base = 0; base < tiles; base += EXP_THREADS * ITEMS) {
+    for (int base = 0; base < tiles; base += ESCAN_THREADS * ITEMS) {
         const int i0 = base + tid * ITEMS;
         uint32_t v[ITEMS], tsum = 0;
 #pragma unroll
@@ -432,9 +445,17 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_scan_kernel(const uint32_t
         if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
         uint32_t woff = 0;
+        {
+            // exclusive prefix of the warp totals: one shuffle scan per warp over (up to) 32 totals
+            const uint32_t wv = (lane < ESCAN_WARPS) ? s_warp[lane] : 0u;
+            uint32_t wi = wv;
 #pragma unroll
-        for (int w = 0; w < EXP_WARPS; ++w)
-            if (w < warp) woff += s_warp[w];
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const uint32_t x = __shfl_up_sync(0xffffffffu, wi, dd);
+                if (lane >= dd) wi += x;
+            }
+            woff = __shfl_sync(0xffffffffu, wi - wv, warp);
+        }
         uint32_t r = s_carry + woff + incl - tsum;
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
@@ -446,7 +467,7 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_scan_kernel(const uint32_t
             r += v[j];
         }
         __syncthreads();
-        if (tid == EXP_THREADS - 1) s_carry = r;
+        if (tid == ESCAN_THREADS - 1) s_carry = r;
         __syncthreads();
     }
 }
@@ -738,7 +759,8 @@ int launch_bin_expand(const ExpandPlan& p, cudaStream_t s, cudaEvent_t* ev) {
                                 p.rec_bins, (uint32_t)p.n_records, nbins, t.bin_start));
         ++launches;
     }
-    GSR_CUDA_TRY(launch_pdl(chunk_table_kernel, dim3(1), dim3(TABLE_THREADS), 0, s, nbins, p.bin_counts, t.bin_start,
+    const unsigned table_ctas = std::min(64u, (nchunk_bound + TABLE_THREADS - 1) / TABLE_THREADS);
+    GSR_CUDA_TRY(launch_pdl(chunk_table_kernel, dim3(table_ctas), dim3(TABLE_THREADS), 0, s, nbins, p.bin_counts, t.bin_start,
                             t.bin_chunk_first, t.chunk_desc, t.done_counter));
     ++launches;
     ExpandArgs a;
@@ -762,7 +784,7 @@ int launch_bin_expand(const ExpandPlan& p, cudaStream_t s, cudaEvent_t* ev) {
                             a));
     if (ev) cudaEventRecord(ev[1], s);
     ++launches;
-    GSR_CUDA_TRY(launch_pdl(expand_scan_kernel, dim3(nbins), dim3(EXP_THREADS), 0, s, (const uint32_t*)t.bin_chunk_first,
+    GSR_CUDA_TRY(launch_pdl(expand_scan_kernel, dim3(nbins), dim3(ESCAN_THREADS), 0, s, (const uint32_t*)t.bin_chunk_first,
                             t.chunk_counts, p.tile_counts, p.grid_x, p.grid_y, p.bins_x, nbins,
                             reinterpret_cast<uint2*>(p.ranges), p.r1_quirk ? 1 : 0, t.done_counter));
     ++launches;

@@ -444,6 +444,11 @@ __device__ __forceinline__ u64 sub2(u64 a, u64 b) {
 constexpr int PAIR_UNROLL = GSR_PAIR_UNROLL;
 constexpr int PAIR_THREADS = 128;
 constexpr int PAIR_WARPS = PAIR_THREADS / 32;
+#ifndef GSR_PAIR_DBUF
+#define GSR_PAIR_DBUF 0
+#endif
+constexpr int PAIR_NBUF = GSR_PAIR_DBUF ? 2 : 1;
+static_assert(PAIR_WARPS == 4, "s_done_flags holds one byte per warp");
 static_assert(CBATCH == PAIR_THREADS, "every thread of the pair kernel stages one splat per round");
 #ifndef GSR_PAIR_MINB
 #define GSR_PAIR_MINB 8    // CTAs of 128 threads per SM (64 registers, no spills); measured C2 / C5 blend: 12 CTAs 0.290 /
@@ -451,13 +456,20 @@ static_assert(CBATCH == PAIR_THREADS, "every thread of the pair kernel stages on
 #endif
 template <bool COUNT>
 __global__ void __launch_bounds__(PAIR_THREADS, GSR_PAIR_MINB) blend_pair_kernel(const BlendParams p) {
-    __shared__ float4 s_splat[CBATCH * 3];
-    __shared__ unsigned char s_mask[CBATCH];                  // bit w: splat can reach warp w's 8x8 quadrant
+    // GSR_PAIR_DBUF=1: two staging buffers and ONE barrier per round.  A warp that leaves its candidate walk early stages
+    // its share of the next batch into the other buffer while the slower quadrants are still walking, instead of waiting
+    // for them twice per round (ncu, r02h: 18 % of the stall samples sit on the round barrier, 12 % in the staging code
+    // behind it); once every quadrant has reported done the staging is skipped, so the speculation costs nothing but
+    // issue slots of warps that would otherwise wait.  Same rounds, same arithmetic, identical output.
+    __shared__ float4 s_splat[PAIR_NBUF][CBATCH * 3];
+    __shared__ unsigned char s_mask[PAIR_NBUF][CBATCH];       // bit w: splat can reach warp w's 8x8 quadrant
     __shared__ unsigned short s_list[PAIR_WARPS][CBATCH];     // per warp: shared-window addresses of its candidates' records
+    __shared__ volatile uint32_t s_done_flags;                // DBUF: byte w != 0 once warp w has finished all its pixels
 
     const int tile = (int)blockIdx.x;
     const int tile_x = tile % p.grid_x, tile_y = tile / p.grid_x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (GSR_PAIR_DBUF && tid == 0) s_done_flags = 0;
     const int lx = ((warp & 1) << 3) | (lane & 7), ly = ((warp >> 1) << 3) | (lane >> 3);
     const int pix_x = tile_x * TILE_X + lx, pix_y0 = tile_y * TILE_Y + ly, pix_y1 = pix_y0 + 4;
     const bool inside0 = pix_x < p.W && pix_y0 < p.H, inside1 = pix_x < p.W && pix_y1 < p.H;
@@ -470,8 +482,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, GSR_PAIR_MINB) blend_pair_kernel
     float pixf_x = (float)pix_x;
     u64 npy2 = pk2(-(float)pix_y0, -(float)pix_y1);
     asm volatile("" : "+r"(splat_base), "+r"(list_base), "+f"(t_min), "+f"(pixf_x), "+l"(npy2));
-    if ((splat_base + (uint32_t)(CBATCH * 48)) >> 16) __trap();  // the lists hold 16-bit shared-window addresses
-    const uint32_t rec_bias = splat_base;
+    if ((splat_base + (uint32_t)(PAIR_NBUF * CBATCH * 48)) >> 16) __trap();  // the lists hold 16-bit shared-window addresses
 
     gsr_pdl_wait();
     const uint2 range = reinterpret_cast<const uint2*>(p.ranges)[tile];
@@ -499,9 +510,18 @@ __global__ void __launch_bounds__(PAIR_THREADS, GSR_PAIR_MINB) blend_pair_kernel
         n_c0 = __ldg(col); n_c1 = __ldg(col + 1); n_c2 = __ldg(col + 2);
     }
 
+    if (GSR_PAIR_DBUF) {
+        __syncthreads();  // s_done_flags is cleared
+        if (warp_done && lane == 0) reinterpret_cast<volatile unsigned char*>(&s_done_flags)[warp] = 1;  // quadrant off the image
+    }
     for (int r = 0; r < rounds; ++r) {
-        if (__syncthreads_and(warp_done)) break;
-        if (COUNT && tid == 0) {
+        const int buf = GSR_PAIR_DBUF ? (r & 1) : 0;
+        float4* const sp = s_splat[buf];
+        const uint32_t rec_bias = splat_base + (uint32_t)(buf * CBATCH * 48);
+        if (!GSR_PAIR_DBUF) {
+            if (__syncthreads_and(warp_done)) break;
+        }
+        if (COUNT && !GSR_PAIR_DBUF && tid == 0) {
             atomicAdd(p.counters + 0, 1ull);
             atomicAdd(p.counters + 7, (unsigned long long)min(CBATCH, total - r * CBATCH));
         }
@@ -510,18 +530,20 @@ __global__ void __launch_bounds__(PAIR_THREADS, GSR_PAIR_MINB) blend_pair_kernel
         const float2 xy = n_xy;
         const float4 co = n_co;
         const float cr = n_c0, cg = n_c1, cb = n_c2;
-        if (progress + CBATCH < total) {
+        // DBUF: every quadrant has reported done -> the vote below ends the tile, nothing of this batch will be read
+        const bool stage = !GSR_PAIR_DBUF || s_done_flags != 0x01010101u;
+        if (stage && progress + CBATCH < total) {
             const uint32_t id = __ldg(p.point_list + range.x + progress + CBATCH);
             n_xy = __ldg(reinterpret_cast<const float2*>(p.means2D) + id);
             n_co = __ldg(reinterpret_cast<const float4*>(p.conic_opacity) + id);
             const float* col = p.colors + (size_t)id * 3;
             n_c0 = __ldg(col); n_c1 = __ldg(col + 1); n_c2 = __ldg(col + 2);
         }
-        if (progress < total) {
+        if (stage && progress < total) {
             const float a = co.x, b = co.y, c = co.z, o = co.w;
-            s_splat[3 * tid + 0] = make_float4(xy.x, xy.y, -0.5f * LOG2E * a, -LOG2E * b);
-            s_splat[3 * tid + 1] = make_float4(-0.5f * LOG2E * c, o, cr, cg);
-            s_splat[3 * tid + 2] = make_float4(cb, 0.f, 0.f, 0.f);
+            sp[3 * tid + 0] = make_float4(xy.x, xy.y, -0.5f * LOG2E * a, -LOG2E * b);
+            sp[3 * tid + 1] = make_float4(-0.5f * LOG2E * c, o, cr, cg);
+            sp[3 * tid + 2] = make_float4(cb, 0.f, 0.f, 0.f);
             // which 8x8 quadrants can see this splat with alpha >= 1/255 (same bounds as blend_culled_kernel)
             const float det = a * c - b * b;
             if (!(o >= ALPHA_MIN * 0.999f)) {
@@ -551,14 +573,24 @@ __global__ void __launch_bounds__(PAIR_THREADS, GSR_PAIR_MINB) blend_pair_kernel
                 }
             }
         }
-        s_mask[tid] = (unsigned char)m;
-        __syncthreads();
+        s_mask[buf][tid] = (unsigned char)m;
+        if (GSR_PAIR_DBUF) {
+            // the one barrier of the round: the batch is staged, and every warp has finished the walk of the previous
+            // round (so the buffer staged NEXT round is free); the vote is the one the two-barrier form takes
+            if (__syncthreads_and(warp_done)) break;
+            if (COUNT && tid == 0) {
+                atomicAdd(p.counters + 0, 1ull);
+                atomicAdd(p.counters + 7, (unsigned long long)min(CBATCH, total - r * CBATCH));
+            }
+        } else {
+            __syncthreads();
+        }
 
         if (!warp_done) {
             int n = 0;
 #pragma unroll
             for (int c0 = 0; c0 < CBATCH; c0 += 32) {
-                const bool mine = (s_mask[c0 + lane] >> warp) & 1u;
+                const bool mine = (s_mask[buf][c0 + lane] >> warp) & 1u;
                 const unsigned bits = __ballot_sync(0xffffffffu, mine);
                 if (mine) my_list[n + __popc(bits & lane_lt)] = (unsigned short)(rec_bias + (uint32_t)((c0 + lane) * 48));
                 n += __popc(bits);
@@ -634,6 +666,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, GSR_PAIR_MINB) blend_pair_kernel
             }
             if (last_off0 != 0xffffffffu) last0 = (uint32_t)(r * CBATCH + 1) + (last_off0 - rec_bias) / 48u;
             if (last_off1 != 0xffffffffu) last1 = (uint32_t)(r * CBATCH + 1) + (last_off1 - rec_bias) / 48u;
+            if (GSR_PAIR_DBUF && warp_done && lane == 0)
+                reinterpret_cast<volatile unsigned char*>(&s_done_flags)[warp] = 1;
             if (COUNT) {
                 c_live = __reduce_add_sync(0xffffffffu, c_live);
                 c_cand = __reduce_add_sync(0xffffffffu, c_cand);

@@ -144,6 +144,8 @@ __global__ void __launch_bounds__(PRE_THREADS, GSR_PRE_MINB) preprocess_kernel(c
     uint2 rec = make_uint2(0u, 0u);  // tile rect for the duplication kernel: miny<<16|minx, height<<16|width
     bool need_sh = false;
     float dirx = 0.f, diry = 0.f, dirz = 0.f;
+    uint32_t pf_word = 0;  // prefetch mode 3: the word the 64-byte pull returned (one SH coefficient, used below)
+    bool pf_low = false, pf_have = false;
 
     if (valid) {
         int radius_out = 0;
@@ -202,7 +204,9 @@ __global__ void __launch_bounds__(PRE_THREADS, GSR_PRE_MINB) preprocess_kernel(c
         // per C2 frame (preprocess 0.170 -> 0.167 ms at 1.03, profiles/r02_ab.txt).  GSR_PRE_PREFETCH_MODE 0: both
         // 128-byte lines the 192-byte block touches; 1: only the line it owns entirely (the other 64 bytes share
         // their line with a neighbour that may be culled) — measured SLOWER, 0.177 ms: the demand loads of the
-        // un-prefetched third then wait on DRAM; 2: no prefetch.
+        // un-prefetched third then wait on DRAM; 2: no prefetch; 3 (needs GSR_PRE_SH_LANE=1): the owned line is
+        // prefetched, the shared 64 bytes are pulled by a 4-byte load with a 64-byte L2 fetch hint — no gain
+        // (0.177 vs 0.174 ms, profiles/r02l_ab_C2.txt).
 #ifndef GSR_PRE_PREFETCH_BOUND
 #define GSR_PRE_PREFETCH_BOUND 1.03f
 #endif
@@ -214,7 +218,19 @@ __global__ void __launch_bounds__(PRE_THREADS, GSR_PRE_MINB) preprocess_kernel(c
             const char* shp = reinterpret_cast<const char*>(p.shs + (size_t)idx * p.M * 3);
             // (cp.async.bulk.prefetch.L2 of exactly the block's 192 bytes was tried instead of line prefetches:
             // preprocess 0.169 -> 0.190 ms, profiles/r01f_ab.txt)
-            if (GSR_PRE_PREFETCH_MODE == 0 || p.M * 12 <= 128) {
+            if (GSR_PRE_PREFETCH_MODE == 3 && p.M == 16) {
+                // mode 3: the 128-byte line the block owns entirely is prefetched; the 64 bytes it shares a line with a
+                // neighbour (who may be culled) are pulled by a 4-byte load with a 64-byte L2 fetch hint whose result
+                // nobody reads — no line is fetched on behalf of a Gaussian that may not need it
+                const uintptr_t a = reinterpret_cast<uintptr_t>(shp);
+                const bool low = (a & 127u) == 0;  // block starts a line: owns [0,128) and the first half of the next
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(low ? shp : shp + 64));
+                // (ptxas deletes a load nobody consumes: the word is coefficient 0 / 10.2 of this Gaussian and replaces the
+                // copy the SH evaluation loads again)
+                asm volatile("ld.global.nc.L2::64B.b32 %0, [%1];" : "=r"(pf_word) : "l"(low ? shp + 128 : shp));
+                pf_low = low;
+                pf_have = true;
+            } else if (GSR_PRE_PREFETCH_MODE == 0 || p.M * 12 <= 128) {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(shp));
                 if (p.M * 12 > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(shp + 128));
             } else {
@@ -411,13 +427,89 @@ __global__ void __launch_bounds__(PRE_THREADS, GSR_PRE_MINB) preprocess_kernel(c
         reinterpret_cast<uint2*>(p.tile_rects)[idx] = rec;
     }
 
-    // ---- SH colour: 4 lanes per surviving Gaussian -----------------------------------------
+    // ---- SH colour --------------------------------------------------------------------------------------
+    // GSR_PRE_SH_LANE=1 (A/B, off): every lane evaluates the colour of ITS OWN Gaussian — 12 float4 loads of its 192-byte
+    // block and 48 FMAs, basis factors formed in registers — ~170 warp instructions for 32 Gaussians where the compacting
+    // 4-lane form below issues ~470 (ncu source page, r02h).  Built, bit-identical, measured SLOWER (profiles/r02l_ab_*.txt:
+    // preprocess 0.164 -> 0.174 ms at C2, 0.283 -> 0.295 at C3): a warp-wide LDG.128 then touches 32 different lines where
+    // the 4-lane form touches 16, and the kernel is bound by the L1 / LSU request rate and DRAM (84 % of the measured copy
+    // bandwidth on the bytes it moves), not by the issue slots the shorter form saves.  Same summation tree:
+    //   s_q = fma(b[4q+3],c[4q+3], fma(b[4q+2],c[4q+2], fma(b[4q+1],c[4q+1], b[4q]*c[4q])));  rgb = ((s0+s1)+(s2+s3))+0.5
+#ifndef GSR_PRE_SH_LANE
+#define GSR_PRE_SH_LANE 0
+#endif
+    if (!COMPAT && GSR_PRE_SH_LANE) {
+        if (need_sh) {
+            const int ncoef = min(p.M, (p.D + 1) * (p.D + 1));
+            const float* sp = p.shs + (size_t)idx * p.M * 3;
+            const float x = dirx, y = diry, z = dirz;
+            const float xx = fmul(x, x), yy = fmul(y, y), zz = fmul(z, z);
+            const float xy = fmul(x, y), yz = fmul(y, z), xz = fmul(x, z);
+            float part[4][3];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int nk = max(0, min(4, ncoef - 4 * q));  // active coefficients of this group: 4q .. 4q+nk-1
+                float s[12];
+                if (nk == 4 && vec_sh) {
+                    const float4 a = ldg_f4(sp + 12 * q), b = ldg_f4(sp + 12 * q + 4), cc = ldg_f4(sp + 12 * q + 8);
+                    s[0] = a.x; s[1] = a.y; s[2] = a.z; s[3] = a.w;
+                    s[4] = b.x; s[5] = b.y; s[6] = b.z; s[7] = b.w;
+                    s[8] = cc.x; s[9] = cc.y; s[10] = cc.z; s[11] = cc.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) s[i] = (i < nk * 3) ? __ldg(sp + 12 * q + i) : 0.f;
+                }
+                if (GSR_PRE_PREFETCH_MODE == 3 && pf_have) {  // same bits as the word just loaded (see the prefetch above)
+                    if (q == 0 && !pf_low) s[0] = __uint_as_float(pf_word);
+                    if (q == 2 && pf_low) s[8] = __uint_as_float(pf_word);
+                }
+                float b0, b1, b2, b3;
+                if (q == 0) {
+                    b0 = SH_C0;
+                    b1 = -fmul(SH_C1, y);
+                    b2 = fmul(SH_C1, z);
+                    b3 = -fmul(SH_C1, x);
+                } else if (q == 1) {
+                    b0 = fmul(SH_C2_0, xy);
+                    b1 = fmul(SH_C2_1, yz);
+                    b2 = fmul(SH_C2_2, fsub(fsub(fmul(2.0f, zz), xx), yy));
+                    b3 = fmul(SH_C2_3, xz);
+                } else if (q == 2) {
+                    b0 = fmul(SH_C2_4, fsub(xx, yy));
+                    b1 = fmul(fmul(SH_C3_0, y), fsub(fmul(3.0f, xx), yy));
+                    b2 = fmul(fmul(SH_C3_1, xy), z);
+                    b3 = fmul(fmul(SH_C3_2, y), fsub(fsub(fmul(4.0f, zz), xx), yy));
+                } else {
+                    b0 = fmul(fmul(SH_C3_3, z), fsub(fsub(fmul(2.0f, zz), fmul(3.0f, xx)), fmul(3.0f, yy)));
+                    b1 = fmul(fmul(SH_C3_4, x), fsub(fsub(fmul(4.0f, zz), xx), yy));
+                    b2 = fmul(fmul(SH_C3_5, z), fsub(xx, yy));
+                    b3 = fmul(fmul(SH_C3_6, x), fsub(xx, fmul(3.0f, yy)));
+                }
+                if (nk < 1) b0 = 0.f;
+                if (nk < 2) b1 = 0.f;
+                if (nk < 3) b2 = 0.f;
+                if (nk < 4) b3 = 0.f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    part[q][c] = __fmaf_rn(b3, s[9 + c], __fmaf_rn(b2, s[6 + c], __fmaf_rn(b1, s[3 + c], fmul(b0, s[c]))));
+            }
+            float* o = p.rgb + (size_t)idx * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float v = fadd(fadd(fadd(part[0][c], part[1][c]), fadd(part[2][c], part[3][c])), 0.5f);
+                if (p.clamped) p.clamped[(size_t)idx * 3 + c] = v < 0.f;
+                o[c] = fmaxf(v, 0.f);
+            }
+        }
+    }
+
+    // ---- SH colour (default): 4 lanes per surviving Gaussian -----------------------------------------------
     // Phase 1 (owner thread, all lanes busy, no divergence): the 16 basis factors of the view direction go to
     // shared memory.  Phase 2: lane (slot, q) owns coefficients 4q..4q+3 of survivor `slot` (3 coalesced float4
     // = 48 contiguous bytes, 192 B per Gaussian across the 4 lanes), chains them with FMAs, and a two-step
     // butterfly adds the four partial sums: rgb_c = ((s0 + s1) + (s2 + s3)) + 0.5 with
     // s_q = fma(b3,c3, fma(b2,c2, fma(b1,c1, b0*c0))).  oracle/gsr_oracle.cpp evaluates the same tree.
-    if (!COMPAT) {
+    if (!COMPAT && !GSR_PRE_SH_LANE) {
         const unsigned mask = __ballot_sync(0xffffffffu, need_sh);
         if (mask) {
             const int ncoef = min(p.M, (p.D + 1) * (p.D + 1));

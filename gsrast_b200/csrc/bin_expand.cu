@@ -271,6 +271,13 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, const int lane)
     return x;
 }
 
+// KEYS=false (lean callers, ExpandPlan::keys_out == nullptr): the 64-bit sorted keys are not materialised — the forward
+// pass never reads them back (the tile ranges fall out of the scan) — so the expansion carries Gaussian ids only: no
+// depth gather and no (id, depth) records in the count pass, 4-byte staging and 4 instead of 12 bytes per pair written
+// by the fill pass.  point_list and ranges are the same bits either way.
+template <bool KEYS> struct StagedRec { using type = uint2; };
+template <> struct StagedRec<false> { using type = uint32_t; };
+
 struct ExpandArgs {
     const uint32_t* rec_ids;
     const uint4* chunk_desc;
@@ -294,6 +301,7 @@ struct ExpandArgs {
 #define GSR_COUNT_CHUNKS 2   // chunks per CTA: their dependent load chains (descriptor -> id -> rect, depth) overlap
 #endif
 constexpr int CNT_CHUNKS = GSR_COUNT_CHUNKS;
+template <bool KEYS>
 __global__ void __launch_bounds__(EXP_THREADS) expand_count_kernel(const ExpandArgs a) {
     __shared__ uint32_t s_cnt[CNT_CHUNKS][BIN_TILES];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -323,7 +331,7 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_count_kernel(const ExpandA
 #pragma unroll
     for (int k = 0; k < CNT_CHUNKS; ++k) {
         rect[k] = have[k] ? __ldg(a.tile_rects + id[k]) : make_uint2(0u, 0u);
-        dep[k] = have[k] ? __ldg(a.depths + id[k]) : 0u;
+        dep[k] = (KEYS && have[k]) ? __ldg(a.depths + id[k]) : 0u;
     }
 #pragma unroll
     for (int k = 0; k < CNT_CHUNKS; ++k) {
@@ -333,7 +341,7 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_count_kernel(const ExpandA
         uint64_t m = 0ull;
         if (have[k]) {
             m = bin_mask(rect[k], bx8, by8);
-            a.rec_data[d[k].y + (uint32_t)tid] = make_uint2(id[k], dep[k]);
+            if (KEYS) a.rec_data[d[k].y + (uint32_t)tid] = make_uint2(id[k], dep[k]);
         }
         const uint32_t bl = warp_transpose32((uint32_t)m, lane);
         const uint32_t bh = warp_transpose32((uint32_t)(m >> 32), lane);
@@ -478,7 +486,19 @@ __global__ void __launch_bounds__(ESCAN_THREADS) expand_scan_kernel(const uint32
 // its ballots and appends (id, depth) records to the tile's run in the staging buffer; the buffer is then
 // written out as one contiguous run per tile.  Chunks that emit more than EXP_CAP pairs take several rounds of
 // whole warp-steps.
+template <bool KEYS>
+__device__ __forceinline__ void emit_pair(const ExpandArgs& a, const uint32_t g, const uint32_t tile, const uint2 o) {
+    a.keys_out[g] = ((uint64_t)tile << 32) | (uint64_t)o.y;  // GSCuda.cu:466-471
+    a.vals_out[g] = o.x;
+}
+template <bool KEYS>
+__device__ __forceinline__ void emit_pair(const ExpandArgs& a, const uint32_t g, const uint32_t, const uint32_t o) {
+    a.vals_out[g] = o;
+}
+
+template <bool KEYS>
 __global__ void __launch_bounds__(EXP_THREADS) expand_fill_kernel(const ExpandArgs a) {
+    using Rec = typename StagedRec<KEYS>::type;
     __shared__ uint32_t s_bal[EXP_WS][BIN_TILES];      // ballot of tile t in warp-step ws
     __shared__ uint32_t s_pre[EXP_WS + 1][BIN_TILES];  // pairs of tile t before warp-step ws; [EXP_WS] = chunk total
     __shared__ uint32_t s_wspart[2][EXP_WS];           // pairs of warp-step ws, tiles 0-31 / 32-63
@@ -489,8 +509,8 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_fill_kernel(const ExpandAr
     __shared__ uint32_t s_tileid[BIN_TILES];
     __shared__ uint32_t s_soff[BIN_TILES];             // per round: staged offset of tile t (minus s_pre[ws_a][t])
     __shared__ uint32_t s_gadj[BIN_TILES];             // per round: final position = s_gadj[t] + staged index
-    __shared__ uint2 s_rec[EXP_CHUNK];                 // id, depth bits of the chunk's records
-    __shared__ uint2 s_out[EXP_CAP];                   // staged pairs: id, depth bits
+    __shared__ Rec s_rec[EXP_CHUNK];                   // id (, depth bits) of the chunk's records
+    __shared__ Rec s_out[EXP_CAP];                     // staged pairs: id (, depth bits)
     __shared__ unsigned char s_t[EXP_CAP];             // staged pairs: tile of the bin
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -508,8 +528,11 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_fill_kernel(const ExpandAr
         const uint32_t* bal = a.chunk_ballots + (size_t)c * EXP_WS * BIN_TILES;
         const uint32_t b0 = __ldg(bal + tid), b1 = __ldg(bal + EXP_THREADS + tid);
         const uint32_t r = d.y + (uint32_t)tid;
-        uint2 rec = make_uint2(0u, 0u);
-        if (r < d.z) rec = a.rec_data[r];
+        Rec rec = Rec();
+        if (r < d.z) {
+            if constexpr (KEYS) rec = a.rec_data[r];
+            else rec = __ldg(a.rec_ids + r);
+        }
         uint32_t gb = 0, tile = 0;
         if (tid < BIN_TILES) {
             const int tx = bx8 + (tid & (BIN_SIDE - 1)), ty = by8 + (tid >> BIN_SHIFT);
@@ -593,9 +616,7 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_fill_kernel(const ExpandAr
             for (uint32_t j = tid; j < total; j += EXP_THREADS) {
                 const int tt = s_t[j];
                 const uint32_t g = s_gadj[tt] + j;
-                const uint2 o2 = s_out[j ^ ((j >> 4) & 7u)];
-                a.keys_out[g] = ((uint64_t)s_tileid[tt] << 32) | (uint64_t)o2.y;  // GSCuda.cu:466-471
-                a.vals_out[g] = o2.x;
+                emit_pair<KEYS>(a, g, s_tileid[tt], s_out[j ^ ((j >> 4) & 7u)]);
             }
             return;
         }
@@ -646,9 +667,7 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_fill_kernel(const ExpandAr
             for (uint32_t j = tid; j < total; j += EXP_THREADS) {
                 const int tt = s_t[j];
                 const uint32_t g = s_gadj[tt] + j;
-                const uint2 o2 = s_out[j];
-                a.keys_out[g] = ((uint64_t)s_tileid[tt] << 32) | (uint64_t)o2.y;  // GSCuda.cu:466-471
-                a.vals_out[g] = o2.x;
+                emit_pair<KEYS>(a, g, s_tileid[tt], s_out[j]);
             }
             return;
         }
@@ -730,9 +749,7 @@ __global__ void __launch_bounds__(EXP_THREADS) expand_fill_kernel(const ExpandAr
         for (uint32_t j = tid; j < round_pairs; j += EXP_THREADS) {
             const int tt = s_t[j];
             const uint32_t g = s_gadj[tt] + j;
-            const uint2 o = s_out[j];
-            a.keys_out[g] = ((uint64_t)s_tileid[tt] << 32) | (uint64_t)o.y;  // GSCuda.cu:466-471
-            a.vals_out[g] = o.x;
+            emit_pair<KEYS>(a, g, s_tileid[tt], s_out[j]);
         }
         __syncthreads();
     }
@@ -776,12 +793,16 @@ int launch_bin_expand(const ExpandPlan& p, cudaStream_t s, cudaEvent_t* ev) {
     a.keys_out = p.keys_out;
     a.vals_out = p.vals_out;
     a.grid_x = p.grid_x; a.grid_y = p.grid_y; a.bins_x = p.bins_x;
-    GSR_CARVEOUT(expand_count_kernel, "COUNT", -1);
-    GSR_CARVEOUT(expand_fill_kernel, "FILL", -1);
+    const bool keys = p.keys_out != nullptr;
+    GSR_CARVEOUT(expand_count_kernel<true>, "COUNT", -1);
+    GSR_CARVEOUT(expand_fill_kernel<true>, "FILL", -1);
+    GSR_CARVEOUT(expand_count_kernel<false>, "COUNT", -1);
+    GSR_CARVEOUT(expand_fill_kernel<false>, "FILL", -1);
     GSR_CARVEOUT(expand_scan_kernel, "ESCAN", -1);
     if (ev) cudaEventRecord(ev[0], s);
-    GSR_CUDA_TRY(launch_pdl(expand_count_kernel, dim3((nchunk_bound + CNT_CHUNKS - 1) / CNT_CHUNKS), dim3(EXP_THREADS), 0, s,
-                            a));
+    const dim3 cgrid((nchunk_bound + CNT_CHUNKS - 1) / CNT_CHUNKS);
+    if (keys) GSR_CUDA_TRY(launch_pdl(expand_count_kernel<true>, cgrid, dim3(EXP_THREADS), 0, s, a));
+    else GSR_CUDA_TRY(launch_pdl(expand_count_kernel<false>, cgrid, dim3(EXP_THREADS), 0, s, a));
     if (ev) cudaEventRecord(ev[1], s);
     ++launches;
     GSR_CUDA_TRY(launch_pdl(expand_scan_kernel, dim3(nbins), dim3(ESCAN_THREADS), 0, s, (const uint32_t*)t.bin_chunk_first,
@@ -789,7 +810,8 @@ int launch_bin_expand(const ExpandPlan& p, cudaStream_t s, cudaEvent_t* ev) {
                             reinterpret_cast<uint2*>(p.ranges), p.r1_quirk ? 1 : 0, t.done_counter));
     ++launches;
     if (ev) cudaEventRecord(ev[2], s);
-    GSR_CUDA_TRY(launch_pdl(expand_fill_kernel, dim3(nchunk_bound), dim3(EXP_THREADS), 0, s, a));
+    if (keys) GSR_CUDA_TRY(launch_pdl(expand_fill_kernel<true>, dim3(nchunk_bound), dim3(EXP_THREADS), 0, s, a));
+    else GSR_CUDA_TRY(launch_pdl(expand_fill_kernel<false>, dim3(nchunk_bound), dim3(EXP_THREADS), 0, s, a));
     if (ev) cudaEventRecord(ev[3], s);
     ++launches;
     return launches;

@@ -211,6 +211,10 @@ int gsr_forward_ex(const gsr_forward_args* a) { return gsr::forward_impl(a, null
 
 }  // extern "C"
 
+// GSR_LEAN_KEYS=1: lean calls do not materialise the sorted 64-bit keys (bin_expand.cu, KEYS=false)
+#ifndef GSR_LEAN_KEYS
+#define GSR_LEAN_KEYS 1
+#endif
 // GSR_FUSED_DUP=1: lean calls run the fused duplication (gather + look-back + emit in one kernel)
 #ifndef GSR_FUSED_DUP
 #define GSR_FUSED_DUP 0
@@ -432,7 +436,10 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         ep.grid_x = gx; ep.grid_y = gy; ep.bins_x = bins_x; ep.bins_y = bins_y;
         ep.temp = tile_temp + sort_temp_bytes((size_t)R);
         ep.tile_counts = img.tile_order; ep.ranges = img.ranges;
-        ep.keys_out = bin.point_list_keys; ep.vals_out = bin.point_list;
+        // lean callers (the renderer's private scratch): nothing reads the sorted 64-bit keys back — the ranges come out of
+        // the expansion's scan — so they are not materialised: 8 of the 12 bytes per pair the tile sort writes (GSR_LEAN_KEYS)
+        ep.keys_out = ((a->flags & GSR_FLAG_LEAN_STATE) && GSR_LEAN_KEYS) ? nullptr : bin.point_list_keys;
+        ep.vals_out = bin.point_list;
         ep.r1_quirk = compat && R == 1;
         GSR_STAGE(launch_bin_expand(ep, s, sort_ev ? sort_ev + 12 : nullptr));
         tm.mark();  // 6

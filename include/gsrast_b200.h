@@ -39,12 +39,16 @@ typedef char* (*gsr_alloc_fn)(size_t bytes, void* user);
                                        (the path CUB takes in the reference, GSCuda.cu:794-797) instead of the default
                                        bin expansion (sort per 8x8-tile bin, expand each bin into its tiles); same
                                        output bit for bit; also taken automatically for grids of more than 4096 bins */
-#define GSR_FLAG_LEAN_STATE 0x8u    /* do not materialise the geometry-state fields nothing in this forward pass reads:
+#define GSR_FLAG_LEAN_STATE 0x8u    /* do not materialise state nothing in this forward pass reads back: the geometry fields
                                        cov3D[6P], clamped[3P], tiles_touched[P] and point_offsets[P] (35 B/Gaussian of
                                        stores + the 4 B/Gaussian re-read of the index-order scan; the reference keeps them
                                        for its Inspector and for duplicateWithKeys, apps/gsrast/Inspector.cpp:174-188,
-                                       GSCuda.cu:445).  gsr_renderer_* sets it for its private per-lane scratch;
-                                       gsr_forward* never does on its own */
+                                       GSCuda.cu:445) and, on the default bin-expansion path, the sorted 64-bit keys
+                                       point_list_keys[R] (8 of the 12 B/pair the tile sort writes; the reference re-reads
+                                       them once, in identifyTileRanges GSCuda.cu:504-538 — here the ranges come out of the
+                                       expansion's scan).  point_list, ranges and every output are the same bits.
+                                       gsr_renderer_* sets it for its private per-lane scratch; gsr_forward* never does
+                                       on its own */
 
 #define GSR_FLAG_BLEND_COUNT 0x10u  /* with `timings`: run the counting instantiation of the blend kernel (same arithmetic)
                                        and return its work counters in gsr_stage_times.blend_counters — the unit

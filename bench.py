@@ -45,14 +45,18 @@ WORKLOADS = {
 }
 
 
-def algorithmic_bytes(P, P_visible, P_culled, R, tiles, depth_passes, tile_passes, precomp, Rc=0, survey_passes=6):
+def algorithmic_bytes(P, P_visible, P_culled, R, tiles, depth_passes, tile_passes, precomp, Rc=0, survey_passes=6,
+                      lean=True):
     """Two sets of figures per stage.
     SURVEY.md 8(d) ("survey"): the algorithmic bytes of the REFERENCE's formulation — preprocess 284 B/visible +
     20 B/culled Gaussian; sort = 8 B/pair histogram read + 6 passes x 24 B over the R pairs on 64-bit keys.
     "moved": the bytes THIS design's launches are defined to move: preprocess additionally writes the
     4-byte depth key and the 8-byte tile rect of every Gaussian; depth passes 16 B/Gaussian (the first one 12: ids are
     generated); bin expansion (Rc = (Gaussian, bin) records): duplication writes 8 B/record, every bin-digit pass moves
-    16 B/record, the count pass reads 12 B/record, the fill pass reads 16 B/record and writes the 12 B/pair result;
+    16 B/record; lean callers (the renderer this bench drives: the sorted 64-bit keys are not materialised): the count
+    pass reads id + rect (12 B/record) and writes the ballots (8 B/record), the fill pass reads id + ballots
+    (12 B/record) and writes the 4 B/pair list; full state: the count pass also gathers the depth bits and leaves
+    (id, depth) records (16 + 16 B/record), the fill pass reads 16 B/record and writes the 12 B/pair result;
     radix binning (Rc == 0): tile passes 16 B/pair, the last one 8 + 4 read and 12 written."""
     per_vis = (44 + 12 + 48) if precomp else 284
     d = {
@@ -67,8 +71,8 @@ def algorithmic_bytes(P, P_visible, P_culled, R, tiles, depth_passes, tile_passe
         d.update({
             "duplicate": 20 * P_visible + 8 * Rc,
             "bin_pass": 16 * Rc,
-            "expand_count": 12 * Rc,
-            "expand_fill": 16 * Rc + 12 * R + 4 * tiles,
+            "expand_count": (20 if lean else 32) * Rc,
+            "expand_fill": (12 * Rc + 4 * R if lean else 16 * Rc + 12 * R) + 4 * tiles,
             "ranges": 0,
         })
         d["expand"] = d["expand_count"] + d["expand_fill"] + 8 * tiles

@@ -444,15 +444,19 @@ __device__ __forceinline__ u64 sub2(u64 a, u64 b) {
 constexpr int PAIR_UNROLL = GSR_PAIR_UNROLL;
 constexpr int PAIR_THREADS = 128;
 constexpr int PAIR_WARPS = PAIR_THREADS / 32;
+// Measured (profiles/r02m_ab_*.txt, r02n_ab_*.txt; C2 / C5 / C3 blend ms): two barriers, 8 CTAs/SM 0.252 / 1.024 / 0.949;
+// double-buffered at 8 CTAs/SM 0.264 / 1.018 / 0.984 (the second buffer costs the L1 the gathers live in); at 7 CTAs/SM
+// (72 registers) 0.253 / 0.990 / 0.949 — the default; at 6: 0.265 / 1.033 / 1.000.  Two barriers at 7 and 6 CTAs/SM:
+// 0.252 / 1.019 / 0.948 and 0.258 / 1.037 / 0.981.
 #ifndef GSR_PAIR_DBUF
-#define GSR_PAIR_DBUF 0
+#define GSR_PAIR_DBUF 1
 #endif
 constexpr int PAIR_NBUF = GSR_PAIR_DBUF ? 2 : 1;
 static_assert(PAIR_WARPS == 4, "s_done_flags holds one byte per warp");
 static_assert(CBATCH == PAIR_THREADS, "every thread of the pair kernel stages one splat per round");
 #ifndef GSR_PAIR_MINB
-#define GSR_PAIR_MINB 8    // CTAs of 128 threads per SM (64 registers, no spills); measured C2 / C5 blend: 12 CTAs 0.290 /
-                           // 1.173 ms, 10 CTAs 0.272 / 1.097, 8 CTAs 0.265 / 1.075 (profiles/r02b_ab_*.txt)
+#define GSR_PAIR_MINB (GSR_PAIR_DBUF ? 7 : 8)   // CTAs of 128 threads per SM.  Two-barrier form, measured C2 / C5 blend: 12 CTAs
+                           // 0.290 / 1.173 ms, 10 CTAs 0.272 / 1.097, 8 CTAs (64 registers) 0.265 / 1.075 (profiles/r02b_ab_*.txt)
 #endif
 template <bool COUNT>
 __global__ void __launch_bounds__(PAIR_THREADS, GSR_PAIR_MINB) blend_pair_kernel(const BlendParams p) {
@@ -728,7 +732,7 @@ __global__ void fill_background_kernel(int n, const float* __restrict__ backgrou
 #define GSR_BLEND_PAIR 1
 #endif
 #ifndef GSR_PAIR_CARVEOUT
-#define GSR_PAIR_CARVEOUT 44   // ten 7.3 KB CTAs (+1 KB reserved each) need > 64 KB of shared memory
+#define GSR_PAIR_CARVEOUT (GSR_PAIR_DBUF ? 50 : 44)   // seven 13.6 KB CTAs (+1 KB reserved each): 102 KB; eight 7.3 KB ones: 66 KB
 #endif
 static bool blend_use_pair() {
     static const int v = [] {

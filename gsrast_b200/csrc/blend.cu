@@ -452,7 +452,7 @@ constexpr int PAIR_WARPS = PAIR_THREADS / 32;
 #define GSR_PAIR_DBUF 1
 #endif
 constexpr int PAIR_NBUF = GSR_PAIR_DBUF ? 2 : 1;
-static_assert(PAIR_WARPS == 4, "s_done_flags holds one byte per warp");
+static_assert(PAIR_WARPS <= 32, "s_done_flags holds one bit per warp");
 static_assert(CBATCH == PAIR_THREADS, "every thread of the pair kernel stages one splat per round");
 #ifndef GSR_PAIR_MINB
 #define GSR_PAIR_MINB (GSR_PAIR_DBUF ? 7 : 8)   // CTAs of 128 threads per SM.  Two-barrier form, measured C2 / C5 blend: 12 CTAs
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, GSR_PAIR_MINB) blend_pair_kernel
     __shared__ float4 s_splat[PAIR_NBUF][CBATCH * 3];
     __shared__ unsigned char s_mask[PAIR_NBUF][CBATCH];       // bit w: splat can reach warp w's 8x8 quadrant
     __shared__ unsigned short s_list[PAIR_WARPS][CBATCH];     // per warp: shared-window addresses of its candidates' records
-    __shared__ volatile uint32_t s_done_flags;                // DBUF: byte w != 0 once warp w has finished all its pixels
+    __shared__ uint32_t s_done_flags;                         // DBUF: bit w set once warp w has finished all its pixels (atomics only)
 
     const int tile = (int)blockIdx.x;
     const int tile_x = tile % p.grid_x, tile_y = tile / p.grid_x;
@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, GSR_PAIR_MINB) blend_pair_kernel
 
     if (GSR_PAIR_DBUF) {
         __syncthreads();  // s_done_flags is cleared
-        if (warp_done && lane == 0) reinterpret_cast<volatile unsigned char*>(&s_done_flags)[warp] = 1;  // quadrant off the image
+        if (warp_done && lane == 0) atomicOr(&s_done_flags, 1u << warp);  // quadrant off the image
     }
     for (int r = 0; r < rounds; ++r) {
         const int buf = GSR_PAIR_DBUF ? (r & 1) : 0;
@@ -535,7 +535,12 @@ __global__ void __launch_bounds__(PAIR_THREADS, GSR_PAIR_MINB) blend_pair_kernel
         const float4 co = n_co;
         const float cr = n_c0, cg = n_c1, cb = n_c2;
         // DBUF: every quadrant has reported done -> the vote below ends the tile, nothing of this batch will be read
-        const bool stage = !GSR_PAIR_DBUF || s_done_flags != 0x01010101u;
+        bool stage = true;
+        if (GSR_PAIR_DBUF) {  // a hint read without any ordering (shared-memory atomics on both sides): a stale value stages in vain
+            uint32_t f = 0;
+            if (lane == 0) f = atomicOr(&s_done_flags, 0u);
+            stage = __shfl_sync(0xffffffffu, f, 0) != (1u << PAIR_WARPS) - 1u;
+        }
         if (stage && progress + CBATCH < total) {
             const uint32_t id = __ldg(p.point_list + range.x + progress + CBATCH);
             n_xy = __ldg(reinterpret_cast<const float2*>(p.means2D) + id);
@@ -670,8 +675,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, GSR_PAIR_MINB) blend_pair_kernel
             }
             if (last_off0 != 0xffffffffu) last0 = (uint32_t)(r * CBATCH + 1) + (last_off0 - rec_bias) / 48u;
             if (last_off1 != 0xffffffffu) last1 = (uint32_t)(r * CBATCH + 1) + (last_off1 - rec_bias) / 48u;
-            if (GSR_PAIR_DBUF && warp_done && lane == 0)
-                reinterpret_cast<volatile unsigned char*>(&s_done_flags)[warp] = 1;
+            if (GSR_PAIR_DBUF && warp_done && lane == 0) atomicOr(&s_done_flags, 1u << warp);
             if (COUNT) {
                 c_live = __reduce_add_sync(0xffffffffu, c_live);
                 c_cand = __reduce_add_sync(0xffffffffu, c_cand);

@@ -215,6 +215,10 @@ int gsr_forward_ex(const gsr_forward_args* a) { return gsr::forward_impl(a, null
 #ifndef GSR_LEAN_KEYS
 #define GSR_LEAN_KEYS 1
 #endif
+// GSR_LEAN_RADII=1: lean calls that pass no `radii` buffer do not fill internal_radii (4 B/Gaussian of preprocess stores)
+#ifndef GSR_LEAN_RADII
+#define GSR_LEAN_RADII 1
+#endif
 // GSR_FUSED_DUP=1: lean calls run the fused duplication (gather + look-back + emit in one kernel)
 #ifndef GSR_FUSED_DUP
 #define GSR_FUSED_DUP 0
@@ -316,7 +320,10 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
         pp.tile_rects = geom.tile_rects;
         pp.coarse_block_sums = bin_mode ? geom.coarse_block_sums : nullptr;
         const bool lean = (a->flags & GSR_FLAG_LEAN_STATE) != 0;
-        if (lean) { pp.cov3D = nullptr; pp.clamped = nullptr; pp.tiles_touched = nullptr; }
+        if (lean) {
+            pp.cov3D = nullptr; pp.clamped = nullptr; pp.tiles_touched = nullptr;
+            if (GSR_LEAN_RADII && !a->radii) pp.radii = nullptr;  // no caller buffer: internal_radii has no reader either
+        }
         // lean callers need no point_offsets, so the duplication can gather its rects and find its offsets itself
         // (binning.cu, duplicate_sorted_kernel<true>) instead of running behind gather_rects + a single-CTA scan
         fused_sort = lean && GSR_FUSED_SORT != 0;

@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(PRE_THREADS, GSR_PRE_MINB) preprocess_kernel(c
                 cl[0] = 0; cl[1] = 0; cl[2] = 0;
             }
         }
-        p.radii[idx] = radius_out;
+        if (p.radii) p.radii[idx] = radius_out;  // lean callers without a radii buffer: nothing reads internal_radii
         if (p.tiles_touched) p.tiles_touched[idx] = tiles;
         reinterpret_cast<uint2*>(p.tile_rects)[idx] = rec;
     }

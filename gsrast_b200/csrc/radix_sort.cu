@@ -57,6 +57,12 @@ constexpr int MAX_PASSES = 8;
 #define GSR_LOOKBACK_W 8
 #endif
 constexpr int LOOKBACK_W = GSR_LOOKBACK_W;
+// GSR_SORT_UNIFORM: the most significant depth pass counts and ranks whole-warp-uniform steps by vote (UNI below).
+// Measured (profiles/r02r_ab_*.txt): that pass 0.033 -> 0.030 ms at C2, 0.044 -> 0.039 at C3.  The same vote in the
+// histogram kernel (one add per warp for the top digit) made it SLOWER, 0.017 -> 0.020 ms, and was dropped.
+#ifndef GSR_SORT_UNIFORM
+#define GSR_SORT_UNIFORM 1
+#endif
 
 constexpr uint32_t FLAG_AGG = 1u << 30;
 constexpr uint32_t FLAG_INC = 2u << 30;
@@ -181,6 +187,9 @@ struct PassArgs {
     uint2* rect_dst;
     int rect_coarse;
 };
+// UNI (template parameter of the pass, GSR_SORT_UNIFORM): the digit of the pass is expected to be the same for whole
+// warps — the most significant byte of float depth keys takes 3-5 values — so a warp whose 32 items of a step agree
+// counts and ranks them with one vote instead of 32 shared-memory atomics on one address.
 
 // Shared memory: [SORT_TILE] key staging | [SORT_TILE] u32 value staging | per-warp digit counters
 // [SORT_WARPS][RADIX] | per-warp match masks [SORT_WARPS][RADIX] | global bases [RADIX] | misc[16].
@@ -191,7 +200,7 @@ constexpr size_t onesweep_smem() {
 
 // DROP: items whose key is the all-ones pad value are neither counted nor written (the output is compacted);
 // the tile then stages n_stage <= n_tile items.
-template <typename KeyT, bool EXPAND, bool FULL, int SORT_ITEMS, bool DROP, bool RECTS>
+template <typename KeyT, bool EXPAND, bool FULL, int SORT_ITEMS, bool DROP, bool RECTS, bool UNI = false>
 __device__ __forceinline__ void onesweep_tile(const PassArgs& a, const uint32_t n_tile, const uint32_t tile,
                                               unsigned char* s_raw) {
     static_assert(!(DROP && FULL), "a dropping pass tests every item");
@@ -235,7 +244,16 @@ __device__ __forceinline__ void onesweep_tile(const PassArgs& a, const uint32_t 
     for (int i = 0; i < SORT_ITEMS; ++i) {
         // out-of-range items carry the pad key, so in a dropping pass one test covers both
         const bool ok = DROP ? !is_pad(key[i]) : (FULL || (warp_base + i * 32 + lane) < n_tile);
-        if (ok) atomicAdd(&my_hist[digit_of(key[i], shift, dmask)], 1u);
+        const uint32_t d = digit_of(key[i], shift, dmask);
+        if (UNI) {  // every lane takes part in the shuffle and the vote, whatever its `ok`
+            const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
+            const bool same = ok && d == d0;
+            if (__all_sync(0xffffffffu, same)) {
+                if (lane == 0) atomicAdd(&my_hist[d0], 32u);
+                continue;
+            }
+        }
+        if (ok) atomicAdd(&my_hist[d], 1u);
     }
     __syncthreads();
 
@@ -299,7 +317,21 @@ __device__ __forceinline__ void onesweep_tile(const PassArgs& a, const uint32_t 
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; ++i) {
         const bool ok = DROP ? !is_pad(key[i]) : (FULL || (warp_base + i * 32 + lane) < n_tile);
-        uint32_t* slot = my_hist + digit_of(key[i], shift, dmask);
+        const uint32_t dg = digit_of(key[i], shift, dmask);
+        uint32_t* slot = my_hist + dg;
+        if (UNI) {
+            const uint32_t d0 = __shfl_sync(0xffffffffu, dg, 0);  // (not inside the && below: every lane must shuffle)
+            const bool same = ok && dg == d0;
+            if (__all_sync(0xffffffffu, same)) {  // one digit for the whole warp: the ranks are the lane numbers
+                const uint32_t base = slot[0];
+                __syncwarp();
+                if (lane == 0) slot[0] = base + 32u;
+                s_keys[base + lane] = key[i];
+                s_vals[base + lane] = val[i];
+                __syncwarp();
+                continue;
+            }
+        }
         if (ok) atomicOr(slot + SORT_WARPS * RADIX, 1u << lane);
         __syncwarp();
         uint32_t peers = 0, base = 0;
@@ -458,7 +490,7 @@ __device__ __forceinline__ void onesweep_tile(const PassArgs& a, const uint32_t 
     }
 }
 
-template <typename KeyT, bool EXPAND, int MIN_BLOCKS, int SORT_ITEMS, bool DROP = false, bool RECTS = false>
+template <typename KeyT, bool EXPAND, int MIN_BLOCKS, int SORT_ITEMS, bool DROP = false, bool RECTS = false, bool UNI = false>
 __global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) onesweep_kernel(const PassArgs a) {
     constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -481,11 +513,11 @@ __global__ void __launch_bounds__(SORT_THREADS, MIN_BLOCKS) onesweep_kernel(cons
     if (tile_base >= n) return;
     const uint32_t n_tile = (uint32_t)min((size_t)SORT_TILE, n - tile_base);
     if (DROP)
-        onesweep_tile<KeyT, EXPAND, false, SORT_ITEMS, true, RECTS>(a, n_tile, tile, s_raw);
+        onesweep_tile<KeyT, EXPAND, false, SORT_ITEMS, true, RECTS, UNI>(a, n_tile, tile, s_raw);
     else if (n_tile == SORT_TILE)
-        onesweep_tile<KeyT, EXPAND, true, SORT_ITEMS, false, RECTS>(a, n_tile, tile, s_raw);
+        onesweep_tile<KeyT, EXPAND, true, SORT_ITEMS, false, RECTS, UNI>(a, n_tile, tile, s_raw);
     else
-        onesweep_tile<KeyT, EXPAND, false, SORT_ITEMS, false, RECTS>(a, n_tile, tile, s_raw);
+        onesweep_tile<KeyT, EXPAND, false, SORT_ITEMS, false, RECTS, UNI>(a, n_tile, tile, s_raw);
 }
 
 size_t num_sort_tiles(size_t n, int items) { return (n + (size_t)SORT_THREADS * items - 1) / ((size_t)SORT_THREADS * items); }
@@ -538,7 +570,7 @@ int launch_histogram(const KeyT* keys, size_t n, int end_bit, int passes, uint32
     return 1;
 }
 
-template <typename KeyT, bool EXPAND, int MIN_BLOCKS, int ITEMS, bool DROP = false, bool RECTS = false>
+template <typename KeyT, bool EXPAND, int MIN_BLOCKS, int ITEMS, bool DROP = false, bool RECTS = false, bool UNI = false>
 int launch_pass(const PassArgs& a, cudaStream_t s) {
     constexpr size_t smem = onesweep_smem<KeyT, ITEMS>();
     // per-device attribute (one process may drive several GPUs): set once per device and instantiation
@@ -547,12 +579,12 @@ int launch_pass(const PassArgs& a, cudaStream_t s) {
     GSR_CUDA_TRY(cudaGetDevice(&dev));
     const uint64_t bit = 1ull << (dev & 63);
     if (!(configured.load(std::memory_order_acquire) & bit)) {
-        GSR_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS, ITEMS, DROP, RECTS>,
+        GSR_CUDA_TRY(cudaFuncSetAttribute(onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS, ITEMS, DROP, RECTS, UNI>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured.fetch_or(bit, std::memory_order_release);
     }
-    GSR_CARVEOUT((onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS, ITEMS, DROP, RECTS>), "SORT", -1);
-    GSR_CUDA_TRY(launch_pdl(onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS, ITEMS, DROP, RECTS>,
+    GSR_CARVEOUT((onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS, ITEMS, DROP, RECTS, UNI>), "SORT", -1);
+    GSR_CUDA_TRY(launch_pdl(onesweep_kernel<KeyT, EXPAND, MIN_BLOCKS, ITEMS, DROP, RECTS, UNI>,
                             dim3((unsigned)num_sort_tiles(a.n, ITEMS)), dim3(SORT_THREADS), smem, s, a));
     return 1;
 }
@@ -681,6 +713,10 @@ int launch_sort32(const Sort32Plan& p, cudaStream_t s, cudaEvent_t* events) {
                 a.rect_coarse = p.rect_coarse ? 1 : 0;
                 rc = items == ITEMS_SMALL ? launch_pass<uint32_t, false, 6, ITEMS_SMALL, false, true>(a, s)
                                           : launch_pass<uint32_t, false, GSR_MINB_LARGE, ITEMS_LARGE, false, true>(a, s);
+            } else if (GSR_SORT_UNIFORM && p.end_bit == 32 && a.shift == 24) {
+                // most significant byte of a full 32-bit key (float depth bits: sign + 7 exponent bits)
+                rc = items == ITEMS_SMALL ? launch_pass<uint32_t, false, 6, ITEMS_SMALL, false, false, true>(a, s)
+                                          : launch_pass<uint32_t, false, GSR_MINB_LARGE, ITEMS_LARGE, false, false, true>(a, s);
             } else {
                 rc = items == ITEMS_SMALL ? launch_pass<uint32_t, false, 6, ITEMS_SMALL>(a, s)
                                           : launch_pass<uint32_t, false, GSR_MINB_LARGE, ITEMS_LARGE>(a, s);

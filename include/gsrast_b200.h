@@ -40,7 +40,8 @@ typedef char* (*gsr_alloc_fn)(size_t bytes, void* user);
                                        bin expansion (sort per 8x8-tile bin, expand each bin into its tiles); same
                                        output bit for bit; also taken automatically for grids of more than 4096 bins */
 #define GSR_FLAG_LEAN_STATE 0x8u    /* do not materialise state nothing in this forward pass reads back: the geometry fields
-                                       cov3D[6P], clamped[3P], tiles_touched[P] and point_offsets[P] (35 B/Gaussian of
+                                       cov3D[6P], clamped[3P], tiles_touched[P], point_offsets[P] and — when the call
+                                       passes no `radii` buffer — internal_radii[P] (39 B/Gaussian of
                                        stores + the 4 B/Gaussian re-read of the index-order scan; the reference keeps them
                                        for its Inspector and for duplicateWithKeys, apps/gsrast/Inspector.cpp:174-188,
                                        GSCuda.cu:445) and, on the default bin-expansion path, the sorted 64-bit keys

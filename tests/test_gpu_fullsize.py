@@ -51,7 +51,7 @@ def assert_lean_path_identical(sc, cam, full, **kw):
     and the tile ranges must be the same bits as the full-state call's."""
     from gsrast_b200 import _lib
 
-    lean = run_cuda(sc, cam, flags=_lib.FLAG_LEAN_STATE, **kw)
+    lean = run_cuda(sc, cam, flags=_lib.FLAG_LEAN_STATE, radii_external=True, **kw)
     assert lean["num_rendered"] == full["num_rendered"]
     for k in ("radii", "values", "ranges", "n_contrib", "final_T", "out_color"):
         assert np.array_equal(lean[k], full[k]), k

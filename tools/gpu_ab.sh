@@ -13,7 +13,7 @@ for lib in gsrast_b200/variants/lib_*.so; do
   n=$(basename $lib .so)
   envset=""
   for e in $ENVS; do [ "lib_env_${e//[^A-Za-z0-9_]/_}" = "$n" ] && envset="$e"; done
-  env $envset GSRAST_B200_LIB=$PWD/$lib timeout 600 python bench.py --steps ${STEPS:-300} --warmup 10 --no-cpu-baseline --workload ${WL:-C2} > gpurun_out/bench_${n}_$round.log 2>&1
+  env $envset GSRAST_B200_LIB=$PWD/$lib timeout ${BENCH_TIMEOUT:-150} python bench.py --steps ${STEPS:-300} --warmup 10 --no-cpu-baseline --workload ${WL:-C2} > gpurun_out/bench_${n}_$round.log 2>&1
   python - <<PY
 import json
 try:

@@ -17,4 +17,4 @@ for tool in memcheck racecheck synccheck initcheck; do
 done
 timeout 900 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/${TAG}_bench_C2_reference_arm.json 2> gpurun_out/${TAG}_ref.err; tail -c 400 gpurun_out/${TAG}_bench_C2_reference_arm.json
 timeout 600 python tools/blend_stats.py C2 > gpurun_out/${TAG}_blend_stats.txt 2>&1; timeout 600 python tools/blend_stats.py C5 >> gpurun_out/${TAG}_blend_stats.txt 2>&1; cat gpurun_out/${TAG}_blend_stats.txt
-timeout 2400 python -m pytest tests -m gpu -q --timeout 1200 2>&1 | tail -8 > gpurun_out/${TAG}_pytest_gpu.txt; tail -3 gpurun_out/${TAG}_pytest_gpu.txt
+timeout 600 python -m pytest tests -m gpu -q --timeout 120 2>&1 | tail -8 > gpurun_out/${TAG}_pytest_gpu.txt; tail -3 gpurun_out/${TAG}_pytest_gpu.txt

@@ -26,6 +26,16 @@ def _same_lists(a, b):
     assert np.array_equal(a["ranges"], b["ranges"]), "tile ranges"
 
 
+def _lean_same(full, sc, cam, **kw):
+    """The renderer's lean state (GSR_FLAG_LEAN_STATE: the id-only instantiations of the count / fill passes, no sorted
+    64-bit keys) must leave the same sorted Gaussian list, tile ranges and frame."""
+    lean = run_cuda(sc, cam, flags=_lib.FLAG_LEAN_STATE, **kw)
+    assert lean["num_rendered"] == full["num_rendered"]
+    assert np.array_equal(lean["values"], full["values"]), "sorted values (lean)"
+    assert np.array_equal(lean["ranges"], full["ranges"]), "tile ranges (lean)"
+    assert np.array_equal(lean["n_contrib"], full["n_contrib"]) and np.array_equal(lean["out_color"], full["out_color"])
+
+
 @pytest.mark.parametrize("W,H,bin_passes", [(100, 60, 1), (128, 128, 1), (1000, 555, 1), (1920, 1080, 1),
                                             (3840, 2160, 2), (4096, 4200, 2)])
 def test_bin_counts(oracle, W, H, bin_passes):
@@ -43,6 +53,7 @@ def test_bin_counts(oracle, W, H, bin_passes):
     assert t["binning_mode"] == 0 and t["sort_passes"] == 4 + bin_passes
     assert 0 < t["num_coarse"] <= t["num_rendered"]
     _same_lists(cu, run_cuda(sc, cam, flags=_lib.FLAG_RADIX_BINNING))
+    _lean_same(cu, sc, cam)
 
 
 def test_more_than_4096_bins_falls_back(oracle):
@@ -69,6 +80,7 @@ def test_big_splats_multi_round_staging(oracle):
     assert cu["times"]["binning_mode"] == 0
     _same_lists(cu, dict(num_rendered=ref.num_rendered, keys=ref["keys"], values=ref["values"], ranges=ref.ranges))
     _same_lists(cu, run_cuda(sc, cam, flags=_lib.FLAG_RADIX_BINNING))
+    _lean_same(cu, sc, cam)  # the multi-round path of the id-only fill pass
 
 
 def test_depth_ties_and_compat(oracle):
@@ -81,12 +93,14 @@ def test_depth_ties_and_compat(oracle):
     cu = run_cuda(sc, cam)
     ref = run_oracle(oracle, sc, cam)
     _same_lists(cu, dict(num_rendered=ref.num_rendered, keys=ref["keys"], values=ref["values"], ranges=ref.ranges))
+    _lean_same(cu, sc, cam)
     sc2 = S.make_config_scene("C2", P=60_001)[0]
     cam2 = Cm.orbit_cameras(5, 1280, 720)[3]
     a = run_cuda(sc2, cam2, compat=True, use_rects=True)
     b = run_cuda(sc2, cam2, compat=True, use_rects=True, flags=_lib.FLAG_RADIX_BINNING)
     _same_lists(a, b)
     assert np.abs(a["out_color"] - b["out_color"]).max() == 0.0
+    _lean_same(a, sc2, cam2, compat=True, use_rects=True)
 
 
 @pytest.mark.parametrize("P", [1, 2, 31, 33, 511, 513, 2049])
@@ -96,3 +110,5 @@ def test_ragged_record_counts(oracle, P):
     cu = run_cuda(sc, cam)
     ref = run_oracle(oracle, sc, cam)
     assert_parity(cu, ref, check_image=ref.num_rendered > 0)
+    if ref.num_rendered > 0:
+        _lean_same(cu, sc, cam)

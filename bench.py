@@ -93,8 +93,10 @@ class ClockSampler:
     back to `nvidia-smi -lms` when the NVML binding is unavailable)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index=0):
+    def __init__(self, gpu_index=0, period_ms=20.0):
         self.gpu = gpu_index
+        self.period = max(1.0, float(period_ms)) / 1e3
+        self.call_ms = []  # host time of every NVML poll (the driver serialises it against CUDA launches)
         self.sm, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self.thread = None
@@ -105,14 +107,16 @@ class ClockSampler:
             nv.nvmlDeviceGetCurrentClocksThrottleReasons
         while not self._stop.is_set():
             try:
+                t0 = time.perf_counter()
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
                 mask = int(get_reasons(h))
+                self.call_ms.append((time.perf_counter() - t0) * 1e3)
                 for bit, name in self.REASONS.items():
                     if mask & bit:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(self.period)
 
     def start(self):
         try:
@@ -165,8 +169,11 @@ class ClockSampler:
             self.thread.join(timeout=2)
         if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"], "samples": 0}
-        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.sm)}
+        out = {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+               "samples": len(self.sm), "period_ms": self.period * 1e3}
+        if self.call_ms:
+            out["poll_ms"] = {"mean": statistics.mean(self.call_ms), "max": max(self.call_ms)}
+        return out
 
 
 def job_cameras(workload, K, Wm, world, rank, W, H):
@@ -339,6 +346,7 @@ def main():
     ap.add_argument("--no-gather", dest="gather", action="store_false")
     ap.add_argument("--gather-chunk", type=int, default=4, help="views per rank per gather call (overlapped with rendering)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clock-period-ms", type=float, default=20.0, help="NVML clock / throttle-reason polling period")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the in-tree gscuda (oracle/_ref) GPU baseline")
     ap.add_argument("--cpu-frames", type=int, default=3)
     ap.add_argument("--simple-blend", action="store_true")
@@ -414,7 +422,7 @@ def main():
     # ---------------- resident-input throughput (value) -----------------------------------
     render_resident(packed[:Wm])
     barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, period_ms=args.clock_period_ms)
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -440,7 +448,10 @@ def main():
             blk = cam_block[i:i + nhost]
             vr.render_host(blk, tanx, tany, out_host=host_out[: blk.shape[0]])
 
-    render_e2e(packed[:Wm])
+    # Warm-up over the WHOLE landing buffer (nhost views, not Wm): the first DMA into freshly pinned pages is slow on this
+    # box — 16.2 ms for a 20-view call into a new buffer, 14.1-14.2 ms for every later one (tools/e2e_probe.py,
+    # profiles/r02w_e2e_probe.txt) — and a viewer reuses its landing frames for every batch.
+    render_e2e(packed[:max(Wm, nhost)])
     barrier()
     t0 = time.perf_counter()
     render_e2e(packed[Wm:Wm + K])
@@ -461,7 +472,7 @@ def main():
             blk = cam_block[i:i + nhost]
             vr.render_host_u8(blk, tanx, tany, out_host=host_u8[: blk.shape[0]])
 
-    render_e2e_u8(packed[:Wm])
+    render_e2e_u8(packed[:max(Wm, nhost)])
     barrier()
     t0 = time.perf_counter()
     render_e2e_u8(packed[Wm:Wm + K])

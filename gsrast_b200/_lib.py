@@ -27,6 +27,9 @@ ERR_INVALID_ARG = -1000
 ERR_ALLOC_FAILED = -1001
 ERR_TOO_MANY_PAIRS = -1002
 ERR_SORT_STALLED = -1003
+ERR_PLY_OPEN = -1004
+ERR_PLY_FORMAT = -1005
+ERR_PLY_TRUNCATED = -1006
 
 
 class StageTimes(C.Structure):

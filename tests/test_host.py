@@ -167,3 +167,60 @@ def test_numa_placement_is_best_effort():
     else:
         assert os.sched_getaffinity(0) <= before
         os.sched_setaffinity(0, before)
+
+
+def _load_bench():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_bench_byte_model_follows_the_survey():
+    """bench.py rates preprocess on SURVEY 8(d)'s bytes exactly (284 B x visible + 20 B x culled), the reference's sort
+    formulation at 152 B/pair, and — physically — the lean expansion at less than the full-state one."""
+    b = _load_bench()
+    P, vis, R, Rc, tiles = 3_300_000, 2_732_659, 15_515_568, 3_650_085, 8160
+    lean = b.algorithmic_bytes(P, vis, P - vis, R, tiles, 4, 1, False, Rc=Rc, lean=True)
+    full = b.algorithmic_bytes(P, vis, P - vis, R, tiles, 4, 1, False, Rc=Rc, lean=False)
+    assert lean["preprocess"] == 284 * vis + 20 * (P - vis) == 787_421_976
+    assert lean["sort_survey"] == 152 * R
+    assert lean["expand_fill"] < full["expand_fill"] and lean["expand_count"] < full["expand_count"]
+    assert full["expand_fill"] - lean["expand_fill"] == 8 * R + 4 * Rc  # the 64-bit keys and the depth half of the records
+    assert lean["preprocess_moved"] > lean["preprocess"]
+    radix = b.algorithmic_bytes(P, vis, P - vis, R, tiles, 4, 2, False, Rc=0)
+    assert radix["sort_moved"] > lean["sort_moved"]
+
+
+def test_bench_job_cameras_are_the_same_for_both_arms_and_any_step_count():
+    """The views a rank renders depend on (workload, world, rank) only: the reference arm renders what the GPU arm's
+    rank 0 renders, and a different --steps only makes the list longer."""
+    b = _load_bench()
+    short = b.job_cameras("C4", 4, 2, 2, 1, 640, 360)
+    long_ = b.job_cameras("C4", 16, 2, 2, 1, 640, 360)
+    assert len(short) == 6 and len(long_) == 18
+    for a, c in zip(short, long_):
+        assert np.array_equal(a.packed(), c.packed())
+    other = b.job_cameras("C4", 4, 2, 2, 0, 640, 360)
+    assert not np.array_equal(other[0].packed(), short[0].packed())
+    single = b.job_cameras("C2", 3, 1, 1, 0, 640, 360)
+    assert all(np.array_equal(single[0].packed(), c.packed()) for c in single)
+
+
+def test_python_flag_and_error_constants_match_the_header():
+    """gsrast_b200/_lib.py mirrors include/gsrast_b200.h by hand: every GSR_FLAG_* / GSR_ERR_* value must agree."""
+    import re
+
+    from gsrast_b200 import _lib
+
+    text = open(os.path.join(ROOT, "include", "gsrast_b200.h")).read()
+    flags = {m.group(1): int(m.group(2), 16) for m in re.finditer(r"#define\s+GSR_FLAG_(\w+)\s+0x([0-9a-fA-F]+)u", text)}
+    errs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+GSR_ERR_(\w+)\s+\((-\d+)\)", text)}
+    assert len(flags) >= 7 and len(errs) >= 4
+    for name, val in flags.items():
+        assert getattr(_lib, "FLAG_" + name) == val, name
+    for name, val in errs.items():
+        assert getattr(_lib, "ERR_" + name) == val, name
+    assert len(set(flags.values())) == len(flags)  # no two flags share a bit

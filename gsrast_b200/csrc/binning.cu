@@ -228,8 +228,10 @@ __global__ void __launch_bounds__(PRE_THREADS) duplicate_sorted_kernel(
     const int P_all, const int grid_x, const uint32_t* __restrict__ sorted_ids, const uint2* __restrict__ sorted_rects,
     const uint32_t* __restrict__ block_offsets, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
     uint32_t* __restrict__ hist, const int tile_bits, const uint32_t* __restrict__ n_sorted, const int coarse,
-    unsigned long long* __restrict__ fuse_state, const int fuse_blocks, uint32_t* error_flag, const int presorted) {
+    unsigned long long* __restrict__ fuse_state, const int fuse_blocks, uint32_t* error_flag, const int presorted,
+    const int self_offsets) {
     __shared__ uint32_t s_excl[DUP_GAUSS + 1];
+    __shared__ uint32_t s_bpart[PRE_THREADS / 32];
     // 16-byte aligned: the compiler reads the 8 warp sums with LDS.128, which otherwise straddles s_excl[DUP_GAUSS]
     // (unused lane of the vector, but compute-sanitizer racecheck rightly flags the overlap with its later store)
     __shared__ __align__(16) uint32_t s_warp[PRE_THREADS / 32];
@@ -255,7 +257,13 @@ __global__ void __launch_bounds__(PRE_THREADS) duplicate_sorted_kernel(
     const int P = n_sorted ? min(P_all, (int)__ldg(n_sorted)) : P_all;  // depth ranks that exist
     if (block * DUP_GAUSS >= P) return;  // (fused: nothing before this block ever looks at it)
     // every global load of the block is issued here, before anything waits
-    uint32_t boff = FUSED ? 0u : __ldg(block_offsets + block);
+    // self_offsets: `block_offsets` holds the UNSCANNED pair counts of the duplication blocks and every block adds up the
+    // counts before its own (a few coalesced loads per thread, in flight with the rect loads below) — the single-CTA scan
+    // between gather_rects and this kernel leaves the frame's dependency chain (7 us + a launch at C2)
+    uint32_t boff = (FUSED || self_offsets) ? 0u : __ldg(block_offsets + block);
+    uint32_t bpart = 0;
+    if (!FUSED && self_offsets)
+        for (int j = tid; j < block; j += PRE_THREADS) bpart += __ldg(block_offsets + j);
     uint2 rec[DUP_GPT];
     uint32_t gid[DUP_GPT];
     if (FUSED && presorted) {
@@ -324,12 +332,20 @@ __global__ void __launch_bounds__(PRE_THREADS) duplicate_sorted_kernel(
         if (lane >= d) incl += t;
     }
     if (lane == 31) s_warp[warp] = incl;
+    if (!FUSED && self_offsets) {
+        bpart = __reduce_add_sync(0xffffffffu, bpart);
+        if (lane == 0) s_bpart[warp] = bpart;
+    }
     __syncthreads();
     uint32_t woff = 0, total = 0;
 #pragma unroll
     for (int w = 0; w < PRE_THREADS / 32; ++w) {
         if (w < warp) woff += s_warp[w];
         total += s_warp[w];
+    }
+    if (!FUSED && self_offsets) {
+#pragma unroll
+        for (int w = 0; w < PRE_THREADS / 32; ++w) boff += s_bpart[w];
     }
     if (FUSED) {
         // decoupled look-back (warp 0): publish this block's count, add up the counts of the blocks before it until one
@@ -524,14 +540,14 @@ int launch_gather_rects(int P, const uint32_t* sorted_ids, const uint32_t* tile_
 
 int launch_duplicate_sorted(int P, int grid_x, const uint32_t* sorted_ids, const uint32_t* sorted_rects,
                             const uint32_t* block_offsets, uint32_t* keys32_out, uint32_t* vals_out, uint32_t* hist,
-                            int tile_bits, cudaStream_t s, const uint32_t* n_sorted) {
+                            int tile_bits, cudaStream_t s, const uint32_t* n_sorted, bool self_offsets) {
     if (P <= 0) return 0;
     if (tile_bits < 1 || tile_bits > 32) return GSR_ERR_INVALID_ARG;
     const int blocks = num_dup_blocks(P);
     GSR_CARVEOUT(duplicate_sorted_kernel<false>, "DUP", -1);
     duplicate_sorted_kernel<false><<<blocks, PRE_THREADS, 0, s>>>(
         P, grid_x, sorted_ids, reinterpret_cast<const uint2*>(sorted_rects), block_offsets, keys32_out, vals_out, hist,
-        tile_bits, n_sorted, 0, nullptr, 0, nullptr, 0);
+        tile_bits, n_sorted, 0, nullptr, 0, nullptr, 0, self_offsets ? 1 : 0);
     cudaError_t e = cudaPeekAtLastError();
     return e == cudaSuccess ? 1 : -(int)e;
 }
@@ -547,7 +563,7 @@ int launch_duplicate_fused(int P, int grid_x, const uint32_t* sorted_ids, const 
     GSR_CARVEOUT(duplicate_sorted_kernel<true>, "DUP", -1);
     duplicate_sorted_kernel<true><<<blocks, PRE_THREADS, 0, s>>>(
         P, grid_x, sorted_ids, reinterpret_cast<const uint2*>(tile_rects), nullptr, keys32_out, vals_out, hist, tile_bits,
-        n_sorted, coarse ? 1 : 0, static_cast<unsigned long long*>(fuse_state), blocks, error_flag, rects_presorted ? 1 : 0);
+        n_sorted, coarse ? 1 : 0, static_cast<unsigned long long*>(fuse_state), blocks, error_flag, rects_presorted ? 1 : 0, 0);
     cudaError_t e = cudaPeekAtLastError();
     return e == cudaSuccess ? 1 : -(int)e;
 }

@@ -219,6 +219,13 @@ int gsr_forward_ex(const gsr_forward_args* a) { return gsr::forward_impl(a, null
 #ifndef GSR_LEAN_RADII
 #define GSR_LEAN_RADII 1
 #endif
+// GSR_DUP_SELF_OFFSETS=1: the duplication blocks add up the pair counts before their own themselves (no scan launch)
+#ifndef GSR_DUP_SELF_OFFSETS
+#define GSR_DUP_SELF_OFFSETS 1
+#endif
+#ifndef GSR_DUP_SELF_MAX
+#define GSR_DUP_SELF_MAX 4096
+#endif
 // GSR_FUSED_DUP=1: lean calls run the fused duplication (gather + look-back + emit in one kernel)
 #ifndef GSR_FUSED_DUP
 #define GSR_FUSED_DUP 0
@@ -288,7 +295,7 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
     const int depth_passes = sort_num_passes(32);
 
     uint32_t R = 0, Rc = 0;
-    bool fused_dup = false, fused_sort = false;
+    bool fused_dup = false, fused_sort = false, dup_self = false;
     const uint32_t* n_depth = nullptr;  // device: Gaussians the depth sort kept
     uint32_t* sort_error = nullptr;     // device address of the slot's sticky error word
     tm.mark();  // 0
@@ -363,7 +370,11 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
                                       geom.sorted_block_sums, geom.tiles_touched, geom.block_sums,
                                       lean ? nullptr : geom.point_offsets, bin_mode, s, n_depth));
         const int ndb = num_dup_blocks(P);
-        if (!fused_dup) GSR_STAGE(launch_scan_block_sums(geom.sorted_block_sums, ndb, geom.sorted_block_sums + ndb, nullptr, s));
+        // up to GSR_DUP_SELF_MAX duplication blocks (4 M Gaussians; beyond, the quadratic adds cost what the scan does) every block adds up the counts before its own
+        // instead of waiting for a single-CTA scan of them (binning.cu, self_offsets)
+        dup_self = !fused_dup && GSR_DUP_SELF_OFFSETS && ndb <= GSR_DUP_SELF_MAX;
+        if (!fused_dup && !dup_self)
+            GSR_STAGE(launch_scan_block_sums(geom.sorted_block_sums, ndb, geom.sorted_block_sums + ndb, nullptr, s));
         tm.mark();  // 3
         // the one host round trip: num_rendered decides the binning allocation (GSCuda.cu:772,782)
         GSR_CUDA_TRY(cudaEventSynchronize(slot.landed));
@@ -418,7 +429,7 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
                                              n_depth, sort_error, /*rects_presorted=*/fused_sort));
         else
             GSR_STAGE(launch_duplicate_sorted(P, bins_x, geom.depth_sort_ids[1], geom.sorted_rects, geom.sorted_block_sums,
-                                              k32[0], v32[0], bin_hist, bin_bits, s, n_depth));
+                                              k32[0], v32[0], bin_hist, bin_bits, s, n_depth, dup_self));
         tm.mark();  // 4
         const int out = tile_passes & 1;  // one pass: [0] -> [1]; two: [0] -> [1] -> [0]
         {
@@ -459,7 +470,7 @@ int gsr::forward_impl(const gsr_forward_args* a, gsr::HostSlot* slot_in) {
                                              n_depth, sort_error, /*rects_presorted=*/fused_sort));
         else
             GSR_STAGE(launch_duplicate_sorted(P, gx, geom.depth_sort_ids[1], geom.sorted_rects, geom.sorted_block_sums, k32[0],
-                                              v32[0], tile_hist, tile_bits, s, n_depth));
+                                              v32[0], tile_hist, tile_bits, s, n_depth, dup_self));
         tm.mark();  // 4
         {
             Sort32Plan tp;

@@ -82,10 +82,11 @@ int launch_gather_rects(int P, const uint32_t* sorted_ids, const uint32_t* tile_
                         uint32_t* point_offsets, bool coarse, cudaStream_t s, const uint32_t* n_sorted = nullptr);
 // Emits the (tile, Gaussian) pairs of the Gaussians taken in depth order: 32-bit tile keys + Gaussian
 // ids, and accumulates the tile-digit histograms of the following radix passes into `hist`
-// ([passes][256], zeroed).  `block_offsets` = exclusive scan of launch_gather_rects' block_sums.
+// ([passes][256], zeroed).  `block_offsets` = exclusive scan of launch_gather_rects' block_sums, or — self_offsets —
+// those block sums themselves, unscanned (every block then adds up the counts before its own).
 int launch_duplicate_sorted(int P, int grid_x, const uint32_t* sorted_ids, const uint32_t* sorted_rects,
                             const uint32_t* block_offsets, uint32_t* keys32_out, uint32_t* vals_out, uint32_t* hist,
-                            int tile_bits, cudaStream_t s, const uint32_t* n_sorted = nullptr);
+                            int tile_bits, cudaStream_t s, const uint32_t* n_sorted = nullptr, bool self_offsets = false);
 // Fused form for callers that do not need point_offsets: gathers the rects by id itself (tile_rects; coarse = emit
 // (bin, Gaussian) records) — or, rects_presorted, reads them already in depth order and final units from `tile_rects`
 // (the last depth pass of the sort left them there, Sort32Plan::rect_dst) — and finds its offsets by decoupled look-back; `fuse_state` = duplicate_fused_state_bytes(P)

@@ -542,17 +542,19 @@ def main():
     barrier()
     if rank == 0:
         stage_runs = []
-        for i in range(8):
+        for i in range(10):
             _, _, tm = vr.render(packed[Wm:Wm + 1], tanx, tany, out=out_dev[:1], timings=True)
             if i >= 3:
                 stage_runs.append(tm)
         keys = ("preprocess_ms", "scan_ms", "duplicate_ms", "sort_ms", "ranges_ms", "blend_ms", "total_ms",
                 "sort_hist_ms", "depth_sort_ms", "expand_ms", "expand_count_ms", "expand_fill_ms")
-        st = {k: statistics.mean(r[k] for r in stage_runs) for k in keys}
+        # medians of 7 single-lane frames: one hiccup of the box (a 1.7 ms first sort pass in one of five frames of a C3
+        # run, profiles/r02final_bench_C3.json vs _rerun) must not move a stage time, the roofline fraction or latency_fps
+        st = {k: statistics.median(r[k] for r in stage_runs) for k in keys}
         passes = stage_runs[0]["sort_passes"]
         dpasses = stage_runs[0]["depth_passes"]
         tpasses = passes - dpasses
-        pass_ms = [statistics.mean(r["sort_pass_ms"][i] for r in stage_runs) for i in range(passes)]
+        pass_ms = [statistics.median(r["sort_pass_ms"][i] for r in stage_runs) for i in range(passes)]
         R = stage_runs[0]["num_rendered"]
         Rc = stage_runs[0]["num_coarse"] if stage_runs[0]["binning_mode"] == 0 else 0
         launches_per_frame = stage_runs[0]["kernel_launches"]

@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(PRE_THREADS) duplicate_sorted_kernel(
     unsigned long long* __restrict__ fuse_state, const int fuse_blocks, uint32_t* error_flag, const int presorted,
     const int self_offsets) {
     __shared__ uint32_t s_excl[DUP_GAUSS + 1];
-    __shared__ uint32_t s_bpart[PRE_THREADS / 32];
+    __shared__ __align__(16) uint32_t s_bpart[PRE_THREADS / 32];  // 16-byte aligned: read with LDS.128 like s_warp below
     // 16-byte aligned: the compiler reads the 8 warp sums with LDS.128, which otherwise straddles s_excl[DUP_GAUSS]
     // (unused lane of the vector, but compute-sanitizer racecheck rightly flags the overlap with its later store)
     __shared__ __align__(16) uint32_t s_warp[PRE_THREADS / 32];

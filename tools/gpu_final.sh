@@ -1,7 +1,7 @@
 #!/bin/bash
 # What the driver runs at round end + sanitizers on the smoke frame: GPU tests, smoke, both bench arms.
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --timeout 900 2>&1 | tail -15 > gpurun_out/pytest_gpu.log
+timeout 600 python -m pytest tests -m gpu -q --timeout 120 2>&1 | tail -15 > gpurun_out/pytest_gpu.log
 tail -3 gpurun_out/pytest_gpu.log
 for tool in memcheck racecheck; do
   timeout 600 compute-sanitizer --tool $tool --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitizer_$tool.log 2>&1
